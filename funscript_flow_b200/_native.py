@@ -1,0 +1,322 @@
+"""ctypes binding of libffb.so (the C ABI in include/ffb.h).
+
+There is deliberately no fallback: if the CUDA library is missing or no device is usable the
+import of a context raises.  (`load(path)` accepts an explicit path only so the CPU test-suite
+can point it at the g++-built emulation of the same sources under tests/emu/.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.join(_HERE, "libffb.so")
+
+K_NAMES = ["pyramid", "polyexp", "upsample", "flow_iter", "divmag", "radial", "small"]
+K_FLOW_ITER = 3
+
+
+class FFBError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"ffb error {code}: {msg}")
+        self.code = code
+
+
+_libs = {}
+
+
+def load(path: Optional[str] = None) -> C.CDLL:
+    path = os.path.abspath(path or os.environ.get("FFB_LIB") or DEFAULT_LIB)
+    if path in _libs:
+        return _libs[path]
+    if not os.path.exists(path):
+        raise FileNotFoundError(
+            f"{path} not found: build it with `python -m funscript_flow_b200.build` (needs nvcc). "
+            "There is no CPU fallback.")
+    lib = C.CDLL(path)
+    vp, i32, u8p, f32p, f64p, i32p, sz = (C.c_void_p, C.c_int, C.POINTER(C.c_uint8), C.POINTER(C.c_float),
+                                          C.POINTER(C.c_double), C.POINTER(C.c_int32), C.c_size_t)
+    sig = {
+        "ffb_version": (i32, []),
+        "ffb_device_count": (i32, [i32p]),
+        "ffb_last_error": (C.c_char_p, [vp]),
+        "ffb_create": (i32, [i32, C.POINTER(vp)]),
+        "ffb_destroy": (None, [vp]),
+        "ffb_host_alloc": (i32, [C.POINTER(vp), sz]),
+        "ffb_host_free": (i32, [vp]),
+        "ffb_configure": (i32, [vp, i32, i32, i32, i32]),
+        "ffb_bracket_begin": (i32, [vp, i32, C.c_double]),
+        "ffb_bracket_push": (i32, [vp, vp, i32, sz, sz]),
+        "ffb_bracket_finish": (i32, [vp, i32p, f64p, u8p, i32p, i32p, f32p, f32p, f64p]),
+        "ffb_sync": (i32, [vp]),
+        "ffb_bracket_get_flow": (i32, [vp, i32, f32p]),
+        "ffb_flow_ring_size": (i32, [vp]),
+        "ffb_farneback": (i32, [vp, u8p, u8p, i32, i32, sz, f32p]),
+        "ffb_max_divergence": (i32, [vp, f32p, i32, i32, i32p, i32p, f32p]),
+        "ffb_mean_magnitude": (i32, [vp, f32p, i32, i32, f32p]),
+        "ffb_radial_motion": (i32, [vp, f32p, i32, i32, C.c_double, C.c_double, i32, i32, f64p]),
+        "ffb_level_plan": (i32, [i32, i32, i32p, i32p, i32p, i32p, f64p]),
+        "ffb_stage_pyramid": (i32, [vp, u8p, i32, i32, sz, i32, f32p]),
+        "ffb_stage_polyexp": (i32, [vp, f32p, i32, i32, f32p]),
+        "ffb_stage_update_matrices": (i32, [vp, f32p, f32p, f32p, i32, i32, f32p]),
+        "ffb_stage_flow_iter": (i32, [vp, f32p, f32p, f32p, i32, i32, f32p]),
+        "ffb_stage_upsample_flow": (i32, [vp, f32p, i32, i32, i32, i32, f32p]),
+        "ffb_profile": (i32, [vp, i32]),
+        "ffb_profile_reset": (i32, [vp]),
+        "ffb_kernel_stats": (i32, [vp, i32, C.POINTER(C.c_int64), f64p, f64p]),
+        "ffb_launch_count": (C.c_int64, [vp]),
+        "ffb_kernel_name": (C.c_char_p, [i32]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)   # AttributeError here = the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    lib._ffb_symbols = sorted(sig)
+    _libs[path] = lib
+    return lib
+
+
+def device_count(lib_path: Optional[str] = None) -> int:
+    n = C.c_int32(0)
+    load(lib_path).ffb_device_count(C.byref(n))
+    return int(n.value)
+
+
+def level_plan(width: int, height: int, lib_path: Optional[str] = None):
+    lib = load(lib_path)
+    n = C.c_int32(0)
+    w = (C.c_int32 * 4)()
+    h = (C.c_int32 * 4)()
+    ks = (C.c_int32 * 4)()
+    sg = (C.c_double * 4)()
+    rc = lib.ffb_level_plan(width, height, C.byref(n), w, h, ks, sg)
+    if rc:
+        raise FFBError(rc, "ffb_level_plan")
+    return [dict(w=w[i], h=h[i], ksize=ks[i], sigma=sg[i]) for i in range(n.value)]
+
+
+def _u8(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+def _f32(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+class PinnedBuffer:
+    """Page-locked host memory exposed as a NumPy uint8 array (frames DMA straight out of it)."""
+
+    def __init__(self, shape, lib_path: Optional[str] = None):
+        self._lib = load(lib_path)
+        self.nbytes = int(np.prod(shape))
+        p = C.c_void_p()
+        rc = self._lib.ffb_host_alloc(C.byref(p), self.nbytes)
+        if rc:
+            raise FFBError(rc, "ffb_host_alloc")
+        self._ptr = p
+        self.array = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(self.nbytes,)).reshape(shape)
+
+    def free(self):
+        if self._ptr:
+            self.array = None
+            self._lib.ffb_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class FlowContext:
+    """One GPU, one host thread.  Thin, allocation-free wrappers over the C ABI."""
+
+    def __init__(self, device: int = 0, lib_path: Optional[str] = None):
+        self._lib = load(lib_path)
+        h = C.c_void_p()
+        rc = self._lib.ffb_create(int(device), C.byref(h))
+        if rc:
+            raise FFBError(rc, (self._lib.ffb_last_error(None) or b"").decode())
+        self._h = h
+        self.device = device
+        self.geometry = None
+
+    # -- plumbing
+    def _ck(self, rc: int):
+        if rc:
+            raise FFBError(rc, (self._lib.ffb_last_error(self._h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ffb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- geometry / bracket API
+    def configure(self, width: int, height: int, batch_frames: int = 16, max_bracket_pairs: int = 4096):
+        geo = (int(width), int(height), int(batch_frames), int(max_bracket_pairs))
+        if geo != self.geometry:
+            self._ck(self._lib.ffb_configure(self._h, *geo))
+            self.geometry = geo
+
+    def bracket_begin(self, pov_mode: bool = False, cut_threshold: float = 7.0):
+        self._ck(self._lib.ffb_bracket_begin(self._h, int(bool(pov_mode)), float(cut_threshold)))
+
+    def bracket_push(self, frames: np.ndarray):
+        """frames: uint8 [n, H, W] (or [H, W]); the last axis must be contiguous."""
+        if frames.ndim == 2:
+            frames = frames[None]
+        assert frames.dtype == np.uint8 and frames.ndim == 3 and frames.strides[2] == 1
+        n = frames.shape[0]
+        stride = frames.strides[0] if n > 1 else frames.strides[1] * frames.shape[1]
+        self._ck(self._lib.ffb_bracket_push(self._h, frames.ctypes.data, n, frames.strides[1], stride))
+
+    def bracket_push_ptr(self, ptr: int, n: int, pitch: int, frame_stride: int):
+        """Raw pointer variant (device pointers, e.g. torch_tensor.data_ptr())."""
+        self._ck(self._lib.ffb_bracket_push(self._h, C.c_void_p(ptr), int(n), int(pitch), int(frame_stride)))
+
+    def bracket_finish(self):
+        m = self.geometry[3]
+        out = dict(scalar=np.empty(m, np.float64), cut=np.empty(m, np.uint8), cx=np.empty(m, np.int32),
+                   cy=np.empty(m, np.int32), val=np.empty(m, np.float32), mean_mag=np.empty(m, np.float32),
+                   centers=np.empty((m, 2), np.float64))
+        n = C.c_int32(0)
+        self._ck(self._lib.ffb_bracket_finish(
+            self._h, C.byref(n), out["scalar"].ctypes.data_as(C.POINTER(C.c_double)), _u8(out["cut"]),
+            out["cx"].ctypes.data_as(C.POINTER(C.c_int32)), out["cy"].ctypes.data_as(C.POINTER(C.c_int32)),
+            _f32(out["val"]), _f32(out["mean_mag"]), out["centers"].ctypes.data_as(C.POINTER(C.c_double))))
+        k = n.value
+        res = {key: v[:k].copy() for key, v in out.items()}
+        res["cut"] = res["cut"].astype(bool)
+        res["n_pairs"] = k
+        return res
+
+    def sync(self):
+        self._ck(self._lib.ffb_sync(self._h))
+
+    def get_flow(self, pair: int) -> np.ndarray:
+        w, h = self.geometry[:2]
+        out = np.empty((h, w, 2), np.float32)
+        self._ck(self._lib.ffb_bracket_get_flow(self._h, int(pair), _f32(out)))
+        return out
+
+    @property
+    def flow_ring_size(self) -> int:
+        return int(self._lib.ffb_flow_ring_size(self._h))
+
+    # -- per-call functions
+    def farneback(self, prev: np.ndarray, nxt: np.ndarray) -> np.ndarray:
+        prev = np.ascontiguousarray(prev, dtype=np.uint8)
+        nxt = np.ascontiguousarray(nxt, dtype=np.uint8)
+        assert prev.shape == nxt.shape and prev.ndim == 2
+        h, w = prev.shape
+        out = np.empty((h, w, 2), np.float32)
+        self._ck(self._lib.ffb_farneback(self._h, _u8(prev), _u8(nxt), w, h, w, _f32(out)))
+        self.geometry = None   # per-call functions may re-configure the context
+        return out
+
+    def max_divergence(self, flow: np.ndarray):
+        flow = np.ascontiguousarray(flow, dtype=np.float32)
+        h, w = flow.shape[:2]
+        x, y, v = C.c_int32(), C.c_int32(), C.c_float()
+        self._ck(self._lib.ffb_max_divergence(self._h, _f32(flow), w, h, C.byref(x), C.byref(y), C.byref(v)))
+        self.geometry = None
+        return x.value, y.value, np.float32(v.value)
+
+    def mean_magnitude(self, flow: np.ndarray) -> np.float32:
+        flow = np.ascontiguousarray(flow, dtype=np.float32)
+        h, w = flow.shape[:2]
+        v = C.c_float()
+        self._ck(self._lib.ffb_mean_magnitude(self._h, _f32(flow), w, h, C.byref(v)))
+        self.geometry = None
+        return np.float32(v.value)
+
+    def radial_motion(self, flow: np.ndarray, center, is_cut: bool, pov_mode: bool = False) -> float:
+        flow = np.ascontiguousarray(flow, dtype=np.float32)
+        h, w = flow.shape[:2]
+        v = C.c_double()
+        self._ck(self._lib.ffb_radial_motion(self._h, _f32(flow), w, h, float(center[0]), float(center[1]),
+                                             int(bool(is_cut)), int(bool(pov_mode)), C.byref(v)))
+        self.geometry = None
+        return float(v.value)
+
+    # -- stage hooks
+    def stage_pyramid(self, img: np.ndarray, level_k: int) -> np.ndarray:
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        h, w = img.shape
+        plan = level_plan(w, h, self._lib._name)
+        lv = plan[len(plan) - 1 - level_k]
+        out = np.empty((lv["h"], lv["w"]), np.float32)
+        self._ck(self._lib.ffb_stage_pyramid(self._h, _u8(img), w, h, w, int(level_k), _f32(out)))
+        return out
+
+    def stage_polyexp(self, img: np.ndarray) -> np.ndarray:
+        """f32 [h, w] -> f32 [h, w, 5] (converted from the kernel's 5 planes)."""
+        img = np.ascontiguousarray(img, dtype=np.float32)
+        h, w = img.shape
+        out = np.empty((5, h, w), np.float32)
+        self._ck(self._lib.ffb_stage_polyexp(self._h, _f32(img), w, h, _f32(out)))
+        return np.ascontiguousarray(out.transpose(1, 2, 0))
+
+    @staticmethod
+    def _planes(R: np.ndarray) -> np.ndarray:
+        return np.ascontiguousarray(np.asarray(R, np.float32).transpose(2, 0, 1))
+
+    def stage_update_matrices(self, R0, R1, flow) -> np.ndarray:
+        h, w = R0.shape[:2]
+        p0, p1 = self._planes(R0), self._planes(R1)
+        fl = None if flow is None else np.ascontiguousarray(flow, np.float32)
+        out = np.empty((5, h, w), np.float32)
+        self._ck(self._lib.ffb_stage_update_matrices(self._h, _f32(p0), _f32(p1), None if fl is None else _f32(fl),
+                                                     w, h, _f32(out)))
+        return np.ascontiguousarray(out.transpose(1, 2, 0))
+
+    def stage_flow_iter(self, R0, R1, flow_in) -> np.ndarray:
+        h, w = R0.shape[:2]
+        p0, p1 = self._planes(R0), self._planes(R1)
+        fl = None if flow_in is None else np.ascontiguousarray(flow_in, np.float32)
+        out = np.empty((h, w, 2), np.float32)
+        self._ck(self._lib.ffb_stage_flow_iter(self._h, _f32(p0), _f32(p1), None if fl is None else _f32(fl),
+                                               w, h, _f32(out)))
+        return out
+
+    def stage_upsample_flow(self, flow_c: np.ndarray, w: int, h: int) -> np.ndarray:
+        fc = np.ascontiguousarray(flow_c, np.float32)
+        hc, wc = fc.shape[:2]
+        out = np.empty((h, w, 2), np.float32)
+        self._ck(self._lib.ffb_stage_upsample_flow(self._h, _f32(fc), wc, hc, w, h, _f32(out)))
+        return out
+
+    # -- instrumentation
+    def profile(self, enable: bool):
+        self._ck(self._lib.ffb_profile(self._h, int(enable)))
+
+    def profile_reset(self):
+        self._ck(self._lib.ffb_profile_reset(self._h))
+
+    def kernel_stats(self):
+        out = {}
+        for kid, name in enumerate(K_NAMES):
+            n, ms, by = C.c_int64(), C.c_double(), C.c_double()
+            self._ck(self._lib.ffb_kernel_stats(self._h, kid, C.byref(n), C.byref(ms), C.byref(by)))
+            out[name] = dict(launches=int(n.value), ms=float(ms.value), alg_bytes=float(by.value))
+        return out
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.ffb_launch_count(self._h))

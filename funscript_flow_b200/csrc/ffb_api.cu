@@ -1,0 +1,1066 @@
+// ffb_api.cu -- context, stream plumbing and the extern "C" ABI declared in include/ffb.h.
+//
+// One context = one GPU = one host thread.  Frames flow
+//   host (pageable | pinned) --cudaMemcpyAsync on s_copy, double-buffered--> device u8 staging
+//   --k_pyramid_level / k_polyexp--> per-frame expansion slots (ring of B+1 frames; each frame is
+//     expanded once and used as `next` of pair j-1 and `prev` of pair j: streaming mode)
+//   --k_upsample_flow / k_flow_iter x3 per level--> final-flow ring (B+8 pairs)
+//   --k_divmag / k_phase1_finish--> per-pair centre, value, mean magnitude, cut flag (device arrays)
+//   --k_smooth_centers / k_radial / k_radial_finish (lagging 6 pairs)--> per-pair scalar
+// and only the 1-D per-pair results are copied back at ffb_bracket_finish.
+#include "../../include/ffb.h"
+#include "ffb_kernels.cuh"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <limits>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_create_error;
+
+const char* const kKernelNames[FFB_K_COUNT] = {"k_pyramid_level", "k_polyexp",  "k_upsample_flow", "k_flow_iter",
+                                               "k_divmag",        "k_radial",   "small"};
+
+// ------------------------------------------------------------------ host-side constant builders
+int cv_round(double v) { return (int)nearbyint(v); }   // round-half-even in the default FP mode
+
+struct LevelPlan {
+    int n;
+    int k[FFB_MAX_LEVELS], w[FFB_MAX_LEVELS], h[FFB_MAX_LEVELS], ksize[FFB_MAX_LEVELS];
+    double sigma[FFB_MAX_LEVELS];
+};
+
+// calcOpticalFlowFarneback level geometry for pyr_scale 0.5, levels 3.
+LevelPlan make_plan(int W, int H) {
+    LevelPlan p;
+    int k = 0;
+    double scale = 1.0;
+    while (k < 3) {
+        scale *= 0.5;
+        if (W * scale < 32 || H * scale < 32) break;
+        ++k;
+    }
+    p.n = k + 1;
+    for (int i = 0; i < p.n; ++i) {
+        const int kk = k - i;   // coarsest first
+        double s = 1.0;
+        for (int j = 0; j < kk; ++j) s *= 0.5;
+        const double sigma = (1.0 / s - 1.0) * 0.5;
+        int ks = cv_round(sigma * 5) | 1;
+        if (ks < 3) ks = 3;
+        p.k[i] = kk;
+        p.w[i] = cv_round(W * s);
+        p.h[i] = cv_round(H * s);
+        p.ksize[i] = ks;
+        p.sigma[i] = sigma;
+    }
+    return p;
+}
+
+// cv::getGaussianKernel(ksize, sigma, CV_32F), half kernel.
+FfbTaps make_taps(int ksize, double sigma) {
+    FfbTaps t;
+    memset(&t, 0, sizeof(t));
+    t.r = ksize / 2;
+    if (sigma <= 0 && ksize == 3) {
+        t.k[0] = 0.5f;
+        t.k[1] = 0.25f;
+        return t;
+    }
+    if (sigma <= 0) sigma = ((ksize - 1) * 0.5 - 1) * 0.3 + 0.8;
+    std::vector<double> v(ksize);
+    double sum = 0;
+    for (int i = 0; i < ksize; ++i) {
+        const double x = i - (ksize - 1) * 0.5;
+        v[i] = exp(-0.5 / (sigma * sigma) * x * x);
+        sum += v[i];
+    }
+    for (int i = 0; i <= t.r; ++i) t.k[i] = (float)(v[t.r + i] / sum);
+    return t;
+}
+
+// cv::resize INTER_LINEAR per-axis table.
+void make_linear_table(int dst_n, int src_n, std::vector<int>& idx, std::vector<float>& alpha) {
+    idx.resize(dst_n);
+    alpha.resize(dst_n);
+    const double scale = (double)src_n / dst_n;
+    for (int d = 0; d < dst_n; ++d) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int i0 = (int)floorf(f);
+        f -= (float)i0;
+        if (i0 < 0) { i0 = 0; f = 0.f; }
+        if (i0 >= src_n - 1) { i0 = src_n - 1; f = 0.f; }
+        idx[d] = i0;
+        alpha[d] = f;
+    }
+}
+
+// FarnebackPrepareGaussian(n = 5, sigma = 1.2): taps in float32, inverse moments in double.
+void invert6(double G[6][6], double inv[6][6]) {
+    double a[6][12];
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) { a[i][j] = G[i][j]; a[i][j + 6] = i == j ? 1.0 : 0.0; }
+    for (int c = 0; c < 6; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < 6; ++r) if (fabs(a[r][c]) > fabs(a[piv][c])) piv = r;
+        for (int j = 0; j < 12; ++j) { double t = a[c][j]; a[c][j] = a[piv][j]; a[piv][j] = t; }
+        const double d = a[c][c];
+        for (int j = 0; j < 12; ++j) a[c][j] /= d;
+        for (int r = 0; r < 6; ++r) {
+            if (r == c) continue;
+            const double f = a[r][c];
+            for (int j = 0; j < 12; ++j) a[r][j] -= f * a[c][j];
+        }
+    }
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) inv[i][j] = a[i][j + 6];
+}
+
+FfbPolyConsts make_poly_consts() {
+    const int n = FFB_POLY_N;
+    const double sigma = 1.2;
+    float g[2 * FFB_POLY_N + 1], xg[2 * FFB_POLY_N + 1], xxg[2 * FFB_POLY_N + 1];
+    double s = 0;
+    for (int x = -n; x <= n; ++x) { g[x + n] = (float)exp(-x * x / (2 * sigma * sigma)); s += g[x + n]; }
+    s = 1.0 / s;
+    for (int x = -n; x <= n; ++x) {
+        g[x + n] = (float)(g[x + n] * s);
+        xg[x + n] = (float)(x * g[x + n]);
+        xxg[x + n] = (float)(x * x * g[x + n]);
+    }
+    double G[6][6];
+    memset(G, 0, sizeof(G));
+    for (int y = -n; y <= n; ++y)
+        for (int x = -n; x <= n; ++x) {
+            const float gg = g[y + n] * g[x + n];
+            G[0][0] += gg;
+            G[1][1] += gg * (float)(x * x);
+            G[3][3] += gg * (float)(x * x * x * x);
+            G[5][5] += gg * (float)(x * x * y * y);
+        }
+    G[2][2] = G[0][3] = G[0][4] = G[3][0] = G[4][0] = G[1][1];
+    G[4][4] = G[3][3];
+    G[3][4] = G[4][3] = G[5][5];
+    double inv[6][6];
+    invert6(G, inv);
+    FfbPolyConsts c;
+    for (int i = 0; i <= n; ++i) { c.g[i] = g[n + i]; c.xg[i] = xg[n + i]; c.xxg[i] = xxg[n + i]; }
+    c.ig11 = (float)inv[1][1];
+    c.ig03 = (float)inv[0][3];
+    c.ig33 = (float)inv[3][3];
+    c.ig55 = (float)inv[5][5];
+    return c;
+}
+
+// ------------------------------------------------------------------ context
+struct Level {
+    int k = 0, w = 0, h = 0, ksize = 3;
+    double sigma = 0;
+    int rp = 0;            // R / I row pitch (floats)
+    size_t plane = 0;      // rp * h
+    int fp = 0;            // flow row pitch (float2)
+    size_t r_off = 0;      // float offset of this level inside a frame's expansion slot
+    FfbTaps taps;
+    int RW = 0, RH = 0;    // source window bound of one 32x8 output tile
+    int *xi = nullptr, *yi = nullptr, *uxi = nullptr, *uyi = nullptr;
+    float *xa = nullptr, *ya = nullptr, *uxa = nullptr, *uya = nullptr;
+    float* I = nullptr;    // [B][h][rp]
+    float2 *fA = nullptr, *fB = nullptr;   // [B][h][fp]
+};
+
+struct ProfRec { int kid; double bytes; cudaEvent_t e0, e1; };
+
+}  // namespace
+
+struct ffb_ctx {
+    int device = 0;
+    std::string err;
+    cudaStream_t s_comp = nullptr, s_copy = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_expand[2] = {nullptr, nullptr};
+    FfbPolyConsts poly;
+    // geometry
+    int W = 0, H = 0, B = 0, maxPairs = 0, nlev = 0, S = 0, ring_n = 0, fp0 = 0;
+    Level lev[FFB_MAX_LEVELS];
+    float* R = nullptr;
+    size_t r_slot_floats = 0;
+    float2* ring = nullptr;
+    size_t ring_stride = 0;   // float2 per ring element
+    uint8_t* d_u8[2] = {nullptr, nullptr};
+    uint8_t* h_pin[2] = {nullptr, nullptr};
+    // per-bracket results (device) + partials
+    int *d_cx = nullptr, *d_cy = nullptr;
+    float *d_val = nullptr, *d_mm = nullptr;
+    unsigned char* d_cut = nullptr;
+    double *d_centers = nullptr, *d_scalar = nullptr;
+    unsigned long long* d_pkey = nullptr;
+    double *d_psum = nullptr, *d_rpart = nullptr;
+    int div_nblk = 0, div_rpb = 0, rad_gx = 0, rad_gy = 0, rad_rpb = 0;
+    char* h_res = nullptr;    // pinned result staging
+    // bracket state
+    bool in_bracket = false;
+    int pov = 0;
+    float thr = 7.f;
+    int frames_seen = 0, pairs_done = 0, radial_done = 0, batch_no = 0;
+    // instrumentation
+    bool prof = false;
+    std::vector<ProfRec> recs;
+    std::vector<cudaEvent_t> ev_pool;
+    int64_t k_launches[FFB_K_COUNT] = {0};
+    double k_ms[FFB_K_COUNT] = {0}, k_bytes[FFB_K_COUNT] = {0};
+    int64_t launches = 0;
+};
+
+namespace {
+
+int fail(ffb_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CK(c, call)                                                                                   \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail((c), FFB_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define CKL(c)                                                                                        \
+    do {                                                                                              \
+        cudaError_t e_ = cudaGetLastError();                                                          \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail((c), FFB_E_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define TRY(expr)                   \
+    do {                            \
+        int rc_ = (expr);           \
+        if (rc_ != FFB_OK) return rc_; \
+    } while (0)
+
+template <class T>
+int dev_alloc(ffb_ctx* c, T** p, size_t count) {
+    void* v = nullptr;
+    cudaError_t e = cudaMalloc(&v, count * sizeof(T) + 256);   // +256: vector loads may touch a row's tail
+    if (e != cudaSuccess) return fail(c, FFB_E_NOMEM, "cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+    *p = (T*)v;
+    return FFB_OK;
+}
+template <class T>
+void dev_free(T*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+template <class T>
+int upload_vec(ffb_ctx* c, T** dptr, const std::vector<T>& v) {
+    TRY(dev_alloc(c, dptr, v.size()));
+    CK(c, cudaMemcpy(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return FFB_OK;
+}
+
+// ---- profiling helpers
+void prof_begin(ffb_ctx* c, int kid, double bytes) {
+    c->launches++;
+    c->k_launches[kid]++;
+    c->k_bytes[kid] += bytes;
+    if (!c->prof) return;
+    ProfRec r;
+    r.kid = kid;
+    r.bytes = bytes;
+    for (cudaEvent_t* e : {&r.e0, &r.e1}) {
+        if (!c->ev_pool.empty()) { *e = c->ev_pool.back(); c->ev_pool.pop_back(); }
+        else cudaEventCreate(e);
+    }
+    cudaEventRecord(r.e0, c->s_comp);
+    c->recs.push_back(r);
+}
+void prof_end(ffb_ctx* c) {
+    if (!c->prof) return;
+    cudaEventRecord(c->recs.back().e1, c->s_comp);
+}
+void prof_collect(ffb_ctx* c) {
+    for (ProfRec& r : c->recs) {
+        float ms = 0.f;
+        cudaEventSynchronize(r.e1);
+        cudaEventElapsedTime(&ms, r.e0, r.e1);
+        c->k_ms[r.kid] += ms;
+        c->ev_pool.push_back(r.e0);
+        c->ev_pool.push_back(r.e1);
+    }
+    c->recs.clear();
+}
+
+// ------------------------------------------------------------------ kernel launchers
+constexpr int PYR_TW = 32, PYR_TH = 8;
+
+// Upper bound of the source window (in source pixels) any 32x8 output tile of a level needs.
+void pyramid_window(const std::vector<int>& idx, int dst_n, int src_n, int tile, int r, int* bound) {
+    int best = 0;
+    for (int t0 = 0; t0 < dst_n; t0 += tile) {
+        const int t1 = (t0 + tile < dst_n ? t0 + tile : dst_n) - 1;
+        int hi = idx[t1] + 1;
+        if (hi > src_n - 1) hi = src_n - 1;
+        const int ext = (hi + r) - (idx[t0] - r) + 1;
+        if (ext > best) best = ext;
+    }
+    *bound = best;
+}
+
+int launch_pyramid(ffb_ctx* c, const uint8_t* src, size_t src_stride, int src_pitch, int W, int H, float* dst,
+                   size_t dst_stride, int dp, int w, int h, const int* xi, const float* xa, const int* yi,
+                   const float* ya, const FfbTaps& taps, int RW, int RH, int nframes) {
+    FfbPyrArgs a;
+    a.src = src; a.src_frame_stride = src_stride; a.src_pitch = src_pitch; a.W = W; a.H = H;
+    a.dst = dst; a.dst_frame_stride = dst_stride; a.dp = dp; a.w = w; a.h = h;
+    a.xi = xi; a.xa = xa; a.yi = yi; a.ya = ya; a.taps = taps;
+    a.RWp = ffb_round_up(RW, 4);
+    a.p_off = ffb_round_up(a.RWp * RH, 16);
+    const size_t smem = (size_t)a.p_off + (size_t)RH * PYR_TW * sizeof(float);
+    auto kfn = k_pyramid_level<PYR_TW, PYR_TH>;
+    if (smem > 48 * 1024) CK(c, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((w + PYR_TW - 1) / PYR_TW, (h + PYR_TH - 1) / PYR_TH, nframes);
+    prof_begin(c, FFB_K_PYRAMID, (double)nframes * ((double)W * H + 4.0 * w * h));
+    FFB_LAUNCH(kfn, grid, dim3(PYR_TW * PYR_TH), smem, c->s_comp, a);
+    prof_end(c);
+    CKL(c);
+    return FFB_OK;
+}
+
+int launch_polyexp(ffb_ctx* c, const float* src, size_t src_stride, int sp, int w, int h, FfbRing dst, size_t plane,
+                   int rp, int nframes) {
+    FfbPolyArgs a;
+    a.src = src; a.src_frame_stride = src_stride; a.sp = sp; a.w = w; a.h = h;
+    a.dst = dst; a.plane = plane; a.rp = rp; a.c = c->poly;
+    auto kfn = k_polyexp<32, 8>;
+    dim3 grid((w + 31) / 32, (h + 7) / 8, nframes);
+    prof_begin(c, FFB_K_POLYEXP, (double)nframes * 24.0 * w * h);
+    FFB_LAUNCH(kfn, grid, dim3(256), 0, c->s_comp, a);
+    prof_end(c);
+    CKL(c);
+    return FFB_OK;
+}
+
+int launch_upsample(ffb_ctx* c, const float2* src, size_t src_stride, int sp, int wc, int hc, float2* dst,
+                    size_t dst_stride, int dp, int w, int h, const int* xi, const float* xa, const int* yi,
+                    const float* ya, int npairs) {
+    FfbUpArgs a;
+    a.src = src; a.src_stride = src_stride; a.sp = sp; a.wc = wc; a.hc = hc;
+    a.dst = dst; a.dst_stride = dst_stride; a.dp = dp; a.w = w; a.h = h;
+    a.xi = xi; a.xa = xa; a.yi = yi; a.ya = ya;
+    dim3 grid((w + 31) / 32, (h + 7) / 8, npairs);
+    prof_begin(c, FFB_K_UPSAMPLE, (double)npairs * (8.0 * wc * hc + 8.0 * w * h));
+    FFB_LAUNCH(k_upsample_flow, grid, dim3(256), 0, c->s_comp, a);
+    prof_end(c);
+    CKL(c);
+    return FFB_OK;
+}
+
+constexpr int IT_NT = 128, IT_U = 4;
+
+int launch_flow_iter(ffb_ctx* c, FfbRing R, size_t plane, int rp, int w, int h, const float2* fin, size_t fin_stride,
+                     int fip, FfbRing fout, int fop, int npairs) {
+    FfbIterArgs a;
+    a.R = R; a.plane = plane; a.rp = rp; a.w = w; a.h = h;
+    a.fin = fin; a.fin_stride = fin_stride; a.fip = fip; a.fout = fout; a.fop = fop;
+    const int sw_max = (IT_NT - 2 * FFB_WIN_R) / 4 * 4;
+    const int nstrips = (w + sw_max - 1) / sw_max;
+    a.SW = ffb_round_up((w + nstrips - 1) / nstrips, 4);
+    if (a.SW > sw_max) a.SW = sw_max;
+    const int gx = (w + a.SW - 1) / a.SW;
+    // enough CTAs for ~2 waves of 148 SMs x 3 resident CTAs, but segments of at least 48 rows
+    const int target = 148 * 3 * 2;
+    int nseg = (target + gx * npairs - 1) / (gx * npairs);
+    const int max_seg = h / 48 > 1 ? h / 48 : 1;
+    if (nseg > max_seg) nseg = max_seg;
+    if (nseg < 1) nseg = 1;
+    a.SH = (h + nseg - 1) / nseg;
+    const int gy = (h + a.SH - 1) / a.SH;
+    auto kfn = k_flow_iter<IT_NT, IT_U>;
+    const size_t smem = ffb_flow_iter_smem<IT_NT, IT_U>();
+    static bool attr_set = false;
+    if (!attr_set) {
+        CK(c, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    prof_begin(c, FFB_K_FLOW_ITER, (double)npairs * (fin ? 56.0 : 48.0) * w * h);
+    FFB_LAUNCH(kfn, dim3(gx, gy, npairs), dim3(IT_NT), smem, c->s_comp, a);
+    prof_end(c);
+    CKL(c);
+    return FFB_OK;
+}
+
+// ------------------------------------------------------------------ geometry
+void free_geometry(ffb_ctx* c) {
+    for (int l = 0; l < FFB_MAX_LEVELS; ++l) {
+        Level& L = c->lev[l];
+        dev_free(L.xi); dev_free(L.yi); dev_free(L.uxi); dev_free(L.uyi);
+        dev_free(L.xa); dev_free(L.ya); dev_free(L.uxa); dev_free(L.uya);
+        dev_free(L.I); dev_free(L.fA); dev_free(L.fB);
+        L = Level();
+    }
+    dev_free(c->R); dev_free(c->ring);
+    for (int b = 0; b < 2; ++b) {
+        dev_free(c->d_u8[b]);
+        if (c->h_pin[b]) cudaFreeHost(c->h_pin[b]);
+        c->h_pin[b] = nullptr;
+    }
+    dev_free(c->d_cx); dev_free(c->d_cy); dev_free(c->d_val); dev_free(c->d_mm); dev_free(c->d_cut);
+    dev_free(c->d_centers); dev_free(c->d_scalar); dev_free(c->d_pkey); dev_free(c->d_psum); dev_free(c->d_rpart);
+    if (c->h_res) cudaFreeHost(c->h_res);
+    c->h_res = nullptr;
+    c->W = c->H = c->B = c->maxPairs = c->nlev = 0;
+}
+
+int build_level_tables(ffb_ctx* c, Level& L, int W, int H, int wc, int hc) {
+    std::vector<int> xi, yi;
+    std::vector<float> xa, ya;
+    make_linear_table(L.w, W, xi, xa);
+    make_linear_table(L.h, H, yi, ya);
+    pyramid_window(xi, L.w, W, PYR_TW, L.taps.r, &L.RW);
+    pyramid_window(yi, L.h, H, PYR_TH, L.taps.r, &L.RH);
+    TRY(upload_vec(c, &L.xi, xi)); TRY(upload_vec(c, &L.xa, xa));
+    TRY(upload_vec(c, &L.yi, yi)); TRY(upload_vec(c, &L.ya, ya));
+    if (wc > 0) {
+        make_linear_table(L.w, wc, xi, xa);
+        make_linear_table(L.h, hc, yi, ya);
+        TRY(upload_vec(c, &L.uxi, xi)); TRY(upload_vec(c, &L.uxa, xa));
+        TRY(upload_vec(c, &L.uyi, yi)); TRY(upload_vec(c, &L.uya, ya));
+    }
+    return FFB_OK;
+}
+
+int configure(ffb_ctx* c, int W, int H, int B, int maxPairs) {
+    if (W < 16 || H < 16 || B < 1 || maxPairs < 1 || (double)W * H >= 4294967295.0)
+        return fail(c, FFB_E_INVALID, "ffb_configure: bad geometry %dx%d batch %d pairs %d", W, H, B, maxPairs);
+    if (c->in_bracket) return fail(c, FFB_E_INVALID, "ffb_configure inside a bracket");
+    CK(c, cudaStreamSynchronize(c->s_comp));
+    CK(c, cudaStreamSynchronize(c->s_copy));
+    free_geometry(c);
+    const LevelPlan p = make_plan(W, H);
+    c->W = W; c->H = H; c->B = B; c->maxPairs = maxPairs; c->nlev = p.n;
+    c->S = B + 1;
+    c->ring_n = B + 8;
+    size_t off = 0;
+    for (int l = 0; l < p.n; ++l) {
+        Level& L = c->lev[l];
+        L.k = p.k[l]; L.w = p.w[l]; L.h = p.h[l]; L.ksize = p.ksize[l]; L.sigma = p.sigma[l];
+        L.rp = ffb_round_up(L.w, 4);
+        L.plane = (size_t)L.rp * L.h;
+        L.fp = ffb_round_up(L.w, 4);
+        L.r_off = off;
+        off += 5 * L.plane;
+        off = (off + 63) / 64 * 64;
+        L.taps = make_taps(L.ksize, L.sigma);
+        TRY(build_level_tables(c, L, W, H, l > 0 ? c->lev[l - 1].w : 0, l > 0 ? c->lev[l - 1].h : 0));
+        TRY(dev_alloc(c, &L.I, (size_t)B * L.plane));
+        if (l < p.n - 1 || true) {
+            TRY(dev_alloc(c, &L.fA, (size_t)B * L.fp * L.h));
+            TRY(dev_alloc(c, &L.fB, (size_t)B * L.fp * L.h));
+        }
+    }
+    c->r_slot_floats = off;
+    TRY(dev_alloc(c, &c->R, (size_t)c->S * c->r_slot_floats));
+    c->fp0 = c->lev[p.n - 1].fp;
+    c->ring_stride = (size_t)c->fp0 * H;
+    TRY(dev_alloc(c, &c->ring, (size_t)c->ring_n * c->ring_stride));
+    const size_t fbytes = (size_t)W * H;
+    for (int b = 0; b < 2; ++b) {
+        TRY(dev_alloc(c, &c->d_u8[b], (size_t)B * fbytes));
+        void* hp = nullptr;
+        if (cudaHostAlloc(&hp, (size_t)B * fbytes, cudaHostAllocDefault) != cudaSuccess)
+            return fail(c, FFB_E_NOMEM, "cudaHostAlloc(%zu) failed", (size_t)B * fbytes);
+        c->h_pin[b] = (uint8_t*)hp;
+    }
+    TRY(dev_alloc(c, &c->d_cx, (size_t)maxPairs)); TRY(dev_alloc(c, &c->d_cy, (size_t)maxPairs));
+    TRY(dev_alloc(c, &c->d_val, (size_t)maxPairs)); TRY(dev_alloc(c, &c->d_mm, (size_t)maxPairs));
+    TRY(dev_alloc(c, &c->d_cut, (size_t)maxPairs));
+    TRY(dev_alloc(c, &c->d_centers, (size_t)2 * maxPairs)); TRY(dev_alloc(c, &c->d_scalar, (size_t)maxPairs));
+    // reduction geometry: fixed per configuration so results do not depend on batch composition
+    c->div_rpb = 8;
+    c->div_nblk = (H + c->div_rpb - 1) / c->div_rpb;
+    c->rad_gx = (W + 255) / 256;
+    c->rad_rpb = 32;
+    c->rad_gy = (H + c->rad_rpb - 1) / c->rad_rpb;
+    TRY(dev_alloc(c, &c->d_pkey, (size_t)c->ring_n * c->div_nblk));
+    TRY(dev_alloc(c, &c->d_psum, (size_t)c->ring_n * c->div_nblk));
+    TRY(dev_alloc(c, &c->d_rpart, (size_t)c->ring_n * c->rad_gx * c->rad_gy));
+    void* hr = nullptr;
+    if (cudaHostAlloc(&hr, (size_t)maxPairs * 48 + 256, cudaHostAllocDefault) != cudaSuccess)
+        return fail(c, FFB_E_NOMEM, "cudaHostAlloc(results) failed");
+    c->h_res = (char*)hr;
+    return FFB_OK;
+}
+
+// ------------------------------------------------------------------ the per-batch pipeline
+int expand_frames(ffb_ctx* c, const uint8_t* src, size_t stride, int pitch, int nb, int first_frame) {
+    for (int l = 0; l < c->nlev; ++l) {
+        Level& L = c->lev[l];
+        TRY(launch_pyramid(c, src, stride, pitch, c->W, c->H, L.I, L.plane, L.rp, L.w, L.h, L.xi, L.xa, L.yi, L.ya,
+                           L.taps, L.RW, L.RH, nb));
+        FfbRing dst;
+        dst.base = (char*)(c->R + L.r_off);
+        dst.stride = c->r_slot_floats * sizeof(float);
+        dst.first = first_frame % c->S;
+        dst.mod = c->S;
+        TRY(launch_polyexp(c, L.I, L.plane, L.rp, L.w, L.h, dst, L.plane, L.rp, nb));
+    }
+    return FFB_OK;
+}
+
+int flow_pairs(ffb_ctx* c, int p0, int np) {
+    for (int l = 0; l < c->nlev; ++l) {
+        Level& L = c->lev[l];
+        FfbRing R;
+        R.base = (char*)(c->R + L.r_off);
+        R.stride = c->r_slot_floats * sizeof(float);
+        R.first = p0 % c->S;
+        R.mod = c->S;
+        const size_t fstride = (size_t)L.fp * L.h;
+        const float2* fin = nullptr;
+        if (l > 0) {
+            Level& C = c->lev[l - 1];
+            TRY(launch_upsample(c, C.fB, (size_t)C.fp * C.h, C.fp, C.w, C.h, L.fA, fstride, L.fp, L.w, L.h, L.uxi,
+                                L.uxa, L.uyi, L.uya, np));
+            fin = L.fA;
+        }
+        FfbRing toB{(char*)L.fB, fstride * sizeof(float2), 0, 1 << 30};
+        FfbRing toA{(char*)L.fA, fstride * sizeof(float2), 0, 1 << 30};
+        FfbRing toRing{(char*)c->ring, c->ring_stride * sizeof(float2), p0 % c->ring_n, c->ring_n};
+        const bool last = l == c->nlev - 1;
+        TRY(launch_flow_iter(c, R, L.plane, L.rp, L.w, L.h, fin, fstride, L.fp, toB, L.fp, np));
+        TRY(launch_flow_iter(c, R, L.plane, L.rp, L.w, L.h, L.fB, fstride, L.fp, toA, L.fp, np));
+        TRY(launch_flow_iter(c, R, L.plane, L.rp, L.w, L.h, L.fA, fstride, L.fp, last ? toRing : toB, L.fp, np));
+    }
+    return FFB_OK;
+}
+
+int phase1_reduce(ffb_ctx* c, int p0, int np) {
+    FfbDivArgs d;
+    d.flow = FfbRing{(char*)c->ring, c->ring_stride * sizeof(float2), p0 % c->ring_n, c->ring_n};
+    d.fp = c->fp0; d.w = c->W; d.h = c->H; d.rows_per_block = c->div_rpb;
+    d.pkey = c->d_pkey; d.psum = c->d_psum;
+    prof_begin(c, FFB_K_DIVMAG, (double)np * 8.0 * c->W * c->H);
+    FFB_LAUNCH(k_divmag, dim3(c->div_nblk, 1, np), dim3(256), 0, c->s_comp, d);
+    prof_end(c);
+    CKL(c);
+    FfbP1Args f;
+    f.flow = d.flow; f.fp = c->fp0; f.w = c->W; f.h = c->H;
+    f.pkey = c->d_pkey; f.psum = c->d_psum; f.nblk = c->div_nblk;
+    f.pov = c->pov; f.cut_threshold = c->thr; f.out0 = p0;
+    f.cx = c->d_cx; f.cy = c->d_cy; f.val = c->d_val; f.mean_mag = c->d_mm; f.cut = c->d_cut;
+    prof_begin(c, FFB_K_SMALL, 0);
+    FFB_LAUNCH(k_phase1_finish, dim3(np), dim3(32), 0, c->s_comp, f);
+    prof_end(c);
+    CKL(c);
+    return FFB_OK;
+}
+
+// radial pass for bracket pairs [j0, j1); n = number of pairs known so far (window truncation)
+int radial_range(ffb_ctx* c, int j0, int j1, int n) {
+    while (j0 < j1) {
+        const int cnt = (j1 - j0 < c->ring_n) ? j1 - j0 : c->ring_n;
+        prof_begin(c, FFB_K_SMALL, 0);
+        FFB_LAUNCH(k_smooth_centers, dim3((cnt + 127) / 128), dim3(128), 0, c->s_comp, c->d_cx, c->d_cy, n, j0,
+                   j0 + cnt, c->d_centers);
+        prof_end(c);
+        CKL(c);
+        FfbRadArgs r;
+        r.flow = FfbRing{(char*)c->ring, c->ring_stride * sizeof(float2), j0 % c->ring_n, c->ring_n};
+        r.fp = c->fp0; r.w = c->W; r.h = c->H; r.rows_per_block = c->rad_rpb;
+        r.centers = c->d_centers; r.cut = c->d_cut; r.out0 = j0; r.pov = c->pov; r.partial = c->d_rpart;
+        prof_begin(c, FFB_K_RADIAL, (double)cnt * 8.0 * c->W * c->H);
+        FFB_LAUNCH(k_radial, dim3(c->rad_gx, c->rad_gy, cnt), dim3(256), 0, c->s_comp, r);
+        prof_end(c);
+        CKL(c);
+        prof_begin(c, FFB_K_SMALL, 0);
+        FFB_LAUNCH(k_radial_finish, dim3(cnt), dim3(32), 0, c->s_comp, (const double*)c->d_rpart,
+                   c->rad_gx * c->rad_gy, c->W, c->H, j0, c->d_scalar);
+        prof_end(c);
+        CKL(c);
+        j0 += cnt;
+    }
+    return FFB_OK;
+}
+
+enum PtrKind { PTR_PAGEABLE, PTR_PINNED, PTR_DEVICE };
+PtrKind classify(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return PTR_PAGEABLE;
+    }
+    if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) return PTR_DEVICE;
+    if (at.type == cudaMemoryTypeHost) return PTR_PINNED;
+    return PTR_PAGEABLE;
+}
+
+int process_batch(ffb_ctx* c, const uint8_t* frames, int nb, size_t pitch, size_t stride, PtrKind kind) {
+    const int b = c->batch_no & 1;
+    const size_t fbytes = (size_t)c->W * c->H;
+    const uint8_t* src = frames;
+    size_t s_stride = stride;
+    int s_pitch = (int)pitch;
+    if (kind != PTR_DEVICE) {
+        // staging buffer b was last read by the expansion kernels two batches ago
+        CK(c, cudaStreamWaitEvent(c->s_copy, c->ev_expand[b], 0));
+        if (kind == PTR_PAGEABLE) {
+            CK(c, cudaEventSynchronize(c->ev_h2d[b]));   // previous DMA out of h_pin[b] finished
+            for (int f = 0; f < nb; ++f) {
+                const uint8_t* s = frames + (size_t)f * stride;
+                uint8_t* d = c->h_pin[b] + (size_t)f * fbytes;
+                if (pitch == (size_t)c->W) memcpy(d, s, fbytes);
+                else for (int y = 0; y < c->H; ++y) memcpy(d + (size_t)y * c->W, s + (size_t)y * pitch, c->W);
+            }
+            CK(c, cudaMemcpyAsync(c->d_u8[b], c->h_pin[b], (size_t)nb * fbytes, cudaMemcpyHostToDevice, c->s_copy));
+        } else if (pitch == (size_t)c->W && stride == fbytes) {
+            CK(c, cudaMemcpyAsync(c->d_u8[b], frames, (size_t)nb * fbytes, cudaMemcpyHostToDevice, c->s_copy));
+        } else {
+            for (int f = 0; f < nb; ++f)
+                CK(c, cudaMemcpy2DAsync(c->d_u8[b] + (size_t)f * fbytes, c->W, frames + (size_t)f * stride, pitch, c->W,
+                                        c->H, cudaMemcpyHostToDevice, c->s_copy));
+        }
+        CK(c, cudaEventRecord(c->ev_h2d[b], c->s_copy));
+        CK(c, cudaStreamWaitEvent(c->s_comp, c->ev_h2d[b], 0));
+        src = c->d_u8[b];
+        s_stride = fbytes;
+        s_pitch = c->W;
+    }
+    const int g0 = c->frames_seen;
+    TRY(expand_frames(c, src, s_stride, s_pitch, nb, g0));
+    CK(c, cudaEventRecord(c->ev_expand[b], c->s_comp));
+    const int np = nb - (g0 == 0 ? 1 : 0);
+    if (np > 0) {
+        const int p0 = c->pairs_done;
+        if (p0 + np > c->maxPairs) return fail(c, FFB_E_INVALID, "bracket exceeds max_bracket_pairs=%d", c->maxPairs);
+        TRY(flow_pairs(c, p0, np));
+        TRY(phase1_reduce(c, p0, np));
+        c->pairs_done += np;
+        const int r1 = c->pairs_done - 6;
+        if (r1 > c->radial_done) {
+            TRY(radial_range(c, c->radial_done, r1, c->pairs_done));
+            c->radial_done = r1;
+        }
+    }
+    c->frames_seen += nb;
+    c->batch_no++;
+    return FFB_OK;
+}
+
+int ensure_config(ffb_ctx* c, int w, int h) {
+    if (c->W == w && c->H == h && c->B >= 2) return FFB_OK;
+    return configure(c, w, h, 2, 64);
+}
+
+}  // namespace
+
+namespace {
+struct Scratch {   // frees everything it allocated when the hook returns
+    std::vector<void*> ptrs;
+    ~Scratch() { for (void* p : ptrs) cudaFree(p); }
+    template <class T> int alloc(ffb_ctx* c, T** p, size_t n) {
+        TRY(dev_alloc(c, p, n));
+        ptrs.push_back(*p);
+        return FFB_OK;
+    }
+    template <class T> int upload(ffb_ctx* c, T** p, const T* h, size_t n) {
+        TRY(alloc(c, p, n));
+        CK(c, cudaMemcpy(*p, h, n * sizeof(T), cudaMemcpyHostToDevice));
+        return FFB_OK;
+    }
+};
+}  // namespace
+
+// ======================================================================================
+// extern "C" ABI
+// ======================================================================================
+extern "C" {
+
+int ffb_version(void) { return FFB_VERSION; }
+
+const char* ffb_kernel_name(int kid) { return kid >= 0 && kid < FFB_K_COUNT ? kKernelNames[kid] : "?"; }
+
+int ffb_device_count(int* n) {
+    if (!n) return FFB_E_INVALID;
+    int k = 0;
+    if (cudaGetDeviceCount(&k) != cudaSuccess) { cudaGetLastError(); k = 0; }
+    *n = k;
+    return FFB_OK;
+}
+
+const char* ffb_last_error(const ffb_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int ffb_create(int device, ffb_ctx** out) {
+    if (!out) return FFB_E_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(nullptr, FFB_E_NODEVICE, "no CUDA device available (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= n) return fail(nullptr, FFB_E_INVALID, "device %d out of range (0..%d)", device, n - 1);
+    ffb_ctx* c = new ffb_ctx();
+    c->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking) != cudaSuccess) {
+        const int rc = fail(nullptr, FFB_E_CUDA, "stream creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        delete c;
+        return rc;
+    }
+    for (int b = 0; b < 2; ++b) {
+        cudaEventCreateWithFlags(&c->ev_h2d[b], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&c->ev_expand[b], cudaEventDisableTiming);
+        cudaEventRecord(c->ev_h2d[b], c->s_copy);
+        cudaEventRecord(c->ev_expand[b], c->s_comp);
+    }
+    c->poly = make_poly_consts();
+    *out = c;
+    return FFB_OK;
+}
+
+void ffb_destroy(ffb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->s_comp);
+    cudaStreamSynchronize(c->s_copy);
+    prof_collect(c);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    free_geometry(c);
+    for (int b = 0; b < 2; ++b) { cudaEventDestroy(c->ev_h2d[b]); cudaEventDestroy(c->ev_expand[b]); }
+    cudaStreamDestroy(c->s_comp);
+    cudaStreamDestroy(c->s_copy);
+    delete c;
+}
+
+int ffb_host_alloc(void** p, size_t bytes) {
+    if (!p) return FFB_E_INVALID;
+    return cudaHostAlloc(p, bytes, cudaHostAllocDefault) == cudaSuccess ? FFB_OK : FFB_E_NOMEM;
+}
+int ffb_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? FFB_OK : FFB_E_CUDA; }
+
+int ffb_configure(ffb_ctx* c, int w, int h, int batch_frames, int max_pairs) {
+    if (!c) return FFB_E_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    return configure(c, w, h, batch_frames, max_pairs);
+}
+
+int ffb_bracket_begin(ffb_ctx* c, int pov, double thr) {
+    if (!c || c->W == 0) return fail(c, FFB_E_INVALID, "ffb_bracket_begin before ffb_configure");
+    CK(c, cudaSetDevice(c->device));
+    c->in_bracket = true;
+    c->pov = pov ? 1 : 0;
+    c->thr = (float)thr;
+    c->frames_seen = c->pairs_done = c->radial_done = 0;
+    return FFB_OK;
+}
+
+int ffb_bracket_push(ffb_ctx* c, const uint8_t* frames, int n, size_t pitch, size_t stride) {
+    if (!c || !c->in_bracket) return fail(c, FFB_E_INVALID, "ffb_bracket_push outside a bracket");
+    if (!frames || n < 0 || pitch < (size_t)c->W || stride < pitch * (size_t)(c->H - 1) + c->W)
+        return fail(c, FFB_E_INVALID, "ffb_bracket_push: bad arguments");
+    const PtrKind kind = classify(frames);
+    for (int i = 0; i < n;) {
+        const int nb = n - i < c->B ? n - i : c->B;
+        TRY(process_batch(c, frames + (size_t)i * stride, nb, pitch, stride, kind));
+        i += nb;
+    }
+    return FFB_OK;
+}
+
+int ffb_sync(ffb_ctx* c) {
+    if (!c) return FFB_E_INVALID;
+    CK(c, cudaStreamSynchronize(c->s_copy));
+    CK(c, cudaStreamSynchronize(c->s_comp));
+    return FFB_OK;
+}
+
+int ffb_bracket_finish(ffb_ctx* c, int* n_pairs, double* scalar, uint8_t* cut, int32_t* cx, int32_t* cy, float* val,
+                       float* mean_mag, double* centers) {
+    if (!c || !c->in_bracket) return fail(c, FFB_E_INVALID, "ffb_bracket_finish outside a bracket");
+    const int n = c->pairs_done;
+    if (n > c->radial_done) {
+        TRY(radial_range(c, c->radial_done, n, n));
+        c->radial_done = n;
+    }
+    c->in_bracket = false;
+    if (n_pairs) *n_pairs = n;
+    if (n > 0) {
+        char* h = c->h_res;
+        size_t o = 0;
+        double* h_scalar = (double*)(h + o); o += (size_t)n * 8;
+        double* h_centers = (double*)(h + o); o += (size_t)n * 16;
+        int* h_cx = (int*)(h + o); o += (size_t)n * 4;
+        int* h_cy = (int*)(h + o); o += (size_t)n * 4;
+        float* h_val = (float*)(h + o); o += (size_t)n * 4;
+        float* h_mm = (float*)(h + o); o += (size_t)n * 4;
+        unsigned char* h_cut = (unsigned char*)(h + o);
+        CK(c, cudaMemcpyAsync(h_scalar, c->d_scalar, (size_t)n * 8, cudaMemcpyDeviceToHost, c->s_comp));
+        CK(c, cudaMemcpyAsync(h_centers, c->d_centers, (size_t)n * 16, cudaMemcpyDeviceToHost, c->s_comp));
+        CK(c, cudaMemcpyAsync(h_cx, c->d_cx, (size_t)n * 4, cudaMemcpyDeviceToHost, c->s_comp));
+        CK(c, cudaMemcpyAsync(h_cy, c->d_cy, (size_t)n * 4, cudaMemcpyDeviceToHost, c->s_comp));
+        CK(c, cudaMemcpyAsync(h_val, c->d_val, (size_t)n * 4, cudaMemcpyDeviceToHost, c->s_comp));
+        CK(c, cudaMemcpyAsync(h_mm, c->d_mm, (size_t)n * 4, cudaMemcpyDeviceToHost, c->s_comp));
+        CK(c, cudaMemcpyAsync(h_cut, c->d_cut, (size_t)n, cudaMemcpyDeviceToHost, c->s_comp));
+        CK(c, cudaStreamSynchronize(c->s_comp));
+        if (scalar) memcpy(scalar, h_scalar, (size_t)n * 8);
+        if (centers) memcpy(centers, h_centers, (size_t)n * 16);
+        if (cx) memcpy(cx, h_cx, (size_t)n * 4);
+        if (cy) memcpy(cy, h_cy, (size_t)n * 4);
+        if (val) memcpy(val, h_val, (size_t)n * 4);
+        if (mean_mag) memcpy(mean_mag, h_mm, (size_t)n * 4);
+        if (cut) memcpy(cut, h_cut, (size_t)n);
+    } else {
+        CK(c, cudaStreamSynchronize(c->s_comp));
+    }
+    CK(c, cudaStreamSynchronize(c->s_copy));
+    return FFB_OK;
+}
+
+int ffb_flow_ring_size(const ffb_ctx* c) { return c ? c->ring_n : 0; }
+
+int ffb_bracket_get_flow(ffb_ctx* c, int pair, float* out) {
+    if (!c || !out || c->W == 0) return FFB_E_INVALID;
+    if (pair < 0 || pair >= c->pairs_done || pair < c->pairs_done - c->ring_n)
+        return fail(c, FFB_E_RANGE, "flow of pair %d is not resident (pairs %d, ring %d)", pair, c->pairs_done, c->ring_n);
+    CK(c, cudaStreamSynchronize(c->s_comp));
+    const float2* src = c->ring + (size_t)(pair % c->ring_n) * c->ring_stride;
+    CK(c, cudaMemcpy2D(out, (size_t)c->W * 8, src, (size_t)c->fp0 * 8, (size_t)c->W * 8, c->H, cudaMemcpyDeviceToHost));
+    return FFB_OK;
+}
+
+// ---- per-call functions ------------------------------------------------------------------
+int ffb_farneback(ffb_ctx* c, const uint8_t* prev, const uint8_t* next, int w, int h, size_t pitch, float* flow) {
+    if (!c || !prev || !next || !flow) return FFB_E_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    TRY(ensure_config(c, w, h));
+    TRY(ffb_bracket_begin(c, 0, std::numeric_limits<float>::infinity()));
+    TRY(ffb_bracket_push(c, prev, 1, pitch, pitch * h));
+    TRY(ffb_bracket_push(c, next, 1, pitch, pitch * h));
+    int n = 0;
+    TRY(ffb_bracket_finish(c, &n, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
+    return ffb_bracket_get_flow(c, 0, flow);
+}
+
+static int upload_flow(ffb_ctx* c, const float* flow, int w, int h) {
+    TRY(ensure_config(c, w, h));
+    if (c->in_bracket) return fail(c, FFB_E_INVALID, "per-call function inside a bracket");
+    CK(c, cudaMemcpy2DAsync(c->ring, (size_t)c->fp0 * 8, flow, (size_t)w * 8, (size_t)w * 8, h, cudaMemcpyHostToDevice, c->s_comp));
+    c->pairs_done = 0;   // ring contents no longer belong to a bracket
+    return FFB_OK;
+}
+
+static int flow_stats(ffb_ctx* c, const float* flow, int w, int h, int32_t* x, int32_t* y, float* val, float* mm) {
+    if (!c || !flow) return FFB_E_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    TRY(upload_flow(c, flow, w, h));
+    const int pov = c->pov;
+    const float thr = c->thr;
+    c->pov = 0;
+    c->thr = std::numeric_limits<float>::infinity();
+    const int rc = phase1_reduce(c, 0, 1);
+    c->pov = pov;
+    c->thr = thr;
+    TRY(rc);
+    int hx = 0, hy = 0;
+    float hv = 0, hm = 0;
+    CK(c, cudaMemcpyAsync(&hx, c->d_cx, 4, cudaMemcpyDeviceToHost, c->s_comp));
+    CK(c, cudaMemcpyAsync(&hy, c->d_cy, 4, cudaMemcpyDeviceToHost, c->s_comp));
+    CK(c, cudaMemcpyAsync(&hv, c->d_val, 4, cudaMemcpyDeviceToHost, c->s_comp));
+    CK(c, cudaMemcpyAsync(&hm, c->d_mm, 4, cudaMemcpyDeviceToHost, c->s_comp));
+    CK(c, cudaStreamSynchronize(c->s_comp));
+    if (x) *x = hx;
+    if (y) *y = hy;
+    if (val) *val = hv;
+    if (mm) *mm = hm;
+    return FFB_OK;
+}
+
+int ffb_max_divergence(ffb_ctx* c, const float* flow, int w, int h, int32_t* x, int32_t* y, float* val) {
+    return flow_stats(c, flow, w, h, x, y, val, nullptr);
+}
+int ffb_mean_magnitude(ffb_ctx* c, const float* flow, int w, int h, float* mm) {
+    return flow_stats(c, flow, w, h, nullptr, nullptr, nullptr, mm);
+}
+
+int ffb_radial_motion(ffb_ctx* c, const float* flow, int w, int h, double cx, double cy, int is_cut, int pov, double* out) {
+    if (!c || !flow || !out) return FFB_E_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    if (is_cut) { *out = 0.0; return FFB_OK; }   // F:766-767
+    TRY(upload_flow(c, flow, w, h));
+    const double cen[2] = {cx, cy};
+    const unsigned char zero = 0;
+    CK(c, cudaMemcpyAsync(c->d_centers, cen, 16, cudaMemcpyHostToDevice, c->s_comp));
+    CK(c, cudaMemcpyAsync(c->d_cut, &zero, 1, cudaMemcpyHostToDevice, c->s_comp));
+    FfbRadArgs r;
+    r.flow = FfbRing{(char*)c->ring, c->ring_stride * sizeof(float2), 0, c->ring_n};
+    r.fp = c->fp0; r.w = w; r.h = h; r.rows_per_block = c->rad_rpb;
+    r.centers = c->d_centers; r.cut = c->d_cut; r.out0 = 0; r.pov = pov ? 1 : 0; r.partial = c->d_rpart;
+    prof_begin(c, FFB_K_RADIAL, 8.0 * w * h);
+    FFB_LAUNCH(k_radial, dim3(c->rad_gx, c->rad_gy, 1), dim3(256), 0, c->s_comp, r);
+    prof_end(c);
+    CKL(c);
+    prof_begin(c, FFB_K_SMALL, 0);
+    FFB_LAUNCH(k_radial_finish, dim3(1), dim3(32), 0, c->s_comp, (const double*)c->d_rpart, c->rad_gx * c->rad_gy, w, h, 0,
+               c->d_scalar);
+    prof_end(c);
+    CKL(c);
+    CK(c, cudaMemcpyAsync(out, c->d_scalar, 8, cudaMemcpyDeviceToHost, c->s_comp));
+    CK(c, cudaStreamSynchronize(c->s_comp));
+    return FFB_OK;
+}
+
+// ---- stage hooks ---------------------------------------------------------------------------
+int ffb_level_plan(int W, int H, int* n, int* w, int* h, int* ksize, double* sigma) {
+    if (!n || W < 1 || H < 1) return FFB_E_INVALID;
+    const LevelPlan p = make_plan(W, H);
+    *n = p.n;
+    for (int i = 0; i < p.n; ++i) {
+        if (w) w[i] = p.w[i];
+        if (h) h[i] = p.h[i];
+        if (ksize) ksize[i] = p.ksize[i];
+        if (sigma) sigma[i] = p.sigma[i];
+    }
+    return FFB_OK;
+}
+
+
+int ffb_stage_pyramid(ffb_ctx* c, const uint8_t* img, int W, int H, size_t pitch, int level_k, float* out) {
+    if (!c || !img || !out) return FFB_E_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    const LevelPlan p = make_plan(W, H);
+    int li = -1;
+    for (int i = 0; i < p.n; ++i) if (p.k[i] == level_k) li = i;
+    if (li < 0) return fail(c, FFB_E_INVALID, "level %d does not exist for %dx%d", level_k, W, H);
+    const int w = p.w[li], h = p.h[li];
+    const FfbTaps taps = make_taps(p.ksize[li], p.sigma[li]);
+    std::vector<int> xi, yi;
+    std::vector<float> xa, ya;
+    make_linear_table(w, W, xi, xa);
+    make_linear_table(h, H, yi, ya);
+    int RW, RH;
+    pyramid_window(xi, w, W, PYR_TW, taps.r, &RW);
+    pyramid_window(yi, h, H, PYR_TH, taps.r, &RH);
+    Scratch s;
+    uint8_t* d_img; float* d_out; int *dxi, *dyi; float *dxa, *dya;
+    TRY(s.alloc(c, &d_img, (size_t)W * H));
+    CK(c, cudaMemcpy2D(d_img, W, img, pitch, W, H, cudaMemcpyHostToDevice));
+    TRY(s.alloc(c, &d_out, (size_t)w * h));
+    TRY(s.upload(c, &dxi, xi.data(), xi.size())); TRY(s.upload(c, &dxa, xa.data(), xa.size()));
+    TRY(s.upload(c, &dyi, yi.data(), yi.size())); TRY(s.upload(c, &dya, ya.data(), ya.size()));
+    TRY(launch_pyramid(c, d_img, (size_t)W * H, W, W, H, d_out, (size_t)w * h, w, w, h, dxi, dxa, dyi, dya, taps, RW, RH, 1));
+    CK(c, cudaStreamSynchronize(c->s_comp));
+    CK(c, cudaMemcpy(out, d_out, (size_t)w * h * 4, cudaMemcpyDeviceToHost));
+    return FFB_OK;
+}
+
+int ffb_stage_polyexp(ffb_ctx* c, const float* img, int w, int h, float* out) {
+    if (!c || !img || !out) return FFB_E_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    Scratch s;
+    float *d_in, *d_out;
+    TRY(s.upload(c, &d_in, img, (size_t)w * h));
+    TRY(s.alloc(c, &d_out, (size_t)5 * w * h));
+    FfbRing dst{(char*)d_out, 0, 0, 1};
+    TRY(launch_polyexp(c, d_in, (size_t)w * h, w, w, h, dst, (size_t)w * h, w, 1));
+    CK(c, cudaStreamSynchronize(c->s_comp));
+    CK(c, cudaMemcpy(out, d_out, (size_t)5 * w * h * 4, cudaMemcpyDeviceToHost));
+    return FFB_OK;
+}
+
+int ffb_stage_update_matrices(ffb_ctx* c, const float* R0, const float* R1, const float* flow, int w, int h, float* out) {
+    if (!c || !R0 || !R1 || !out) return FFB_E_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    Scratch s;
+    float *d0, *d1, *dM; float2* df = nullptr;
+    TRY(s.upload(c, &d0, R0, (size_t)5 * w * h));
+    TRY(s.upload(c, &d1, R1, (size_t)5 * w * h));
+    if (flow) TRY(s.upload(c, &df, (const float2*)flow, (size_t)w * h));
+    TRY(s.alloc(c, &dM, (size_t)5 * w * h));
+    FfbMatArgs a{d0, d1, (size_t)w * h, w, w, h, df, w, dM};
+    prof_begin(c, FFB_K_SMALL, 0);
+    FFB_LAUNCH(k_update_matrices, dim3((w + 31) / 32, (h + 7) / 8), dim3(256), 0, c->s_comp, a);
+    prof_end(c);
+    CKL(c);
+    CK(c, cudaStreamSynchronize(c->s_comp));
+    CK(c, cudaMemcpy(out, dM, (size_t)5 * w * h * 4, cudaMemcpyDeviceToHost));
+    return FFB_OK;
+}
+
+int ffb_stage_flow_iter(ffb_ctx* c, const float* R0, const float* R1, const float* flow_in, int w, int h, float* flow_out) {
+    if (!c || !R0 || !R1 || !flow_out) return FFB_E_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    Scratch s;
+    const int rp = ffb_round_up(w, 4);
+    const size_t plane = (size_t)rp * h;
+    float* dR; float2 *dfi = nullptr, *dfo;
+    TRY(s.alloc(c, &dR, 10 * plane));
+    for (int f = 0; f < 2; ++f)
+        for (int ch = 0; ch < 5; ++ch)
+            CK(c, cudaMemcpy2D(dR + (f * 5 + ch) * plane, (size_t)rp * 4, (f ? R1 : R0) + (size_t)ch * w * h, (size_t)w * 4,
+                               (size_t)w * 4, h, cudaMemcpyHostToDevice));
+    if (flow_in) {
+        TRY(s.alloc(c, &dfi, plane));
+        CK(c, cudaMemcpy2D(dfi, (size_t)rp * 8, flow_in, (size_t)w * 8, (size_t)w * 8, h, cudaMemcpyHostToDevice));
+    }
+    TRY(s.alloc(c, &dfo, plane));
+    FfbRing R{(char*)dR, 5 * plane * sizeof(float), 0, 2};
+    FfbRing fo{(char*)dfo, 0, 0, 1};
+    TRY(launch_flow_iter(c, R, plane, rp, w, h, dfi, 0, rp, fo, rp, 1));
+    CK(c, cudaStreamSynchronize(c->s_comp));
+    CK(c, cudaMemcpy2D(flow_out, (size_t)w * 8, dfo, (size_t)rp * 8, (size_t)w * 8, h, cudaMemcpyDeviceToHost));
+    return FFB_OK;
+}
+
+int ffb_stage_upsample_flow(ffb_ctx* c, const float* flow_c, int wc, int hc, int w, int h, float* out) {
+    if (!c || !flow_c || !out) return FFB_E_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    std::vector<int> xi, yi;
+    std::vector<float> xa, ya;
+    make_linear_table(w, wc, xi, xa);
+    make_linear_table(h, hc, yi, ya);
+    Scratch s;
+    float2 *dsrc, *ddst; int *dxi, *dyi; float *dxa, *dya;
+    TRY(s.upload(c, &dsrc, (const float2*)flow_c, (size_t)wc * hc));
+    TRY(s.alloc(c, &ddst, (size_t)w * h));
+    TRY(s.upload(c, &dxi, xi.data(), xi.size())); TRY(s.upload(c, &dxa, xa.data(), xa.size()));
+    TRY(s.upload(c, &dyi, yi.data(), yi.size())); TRY(s.upload(c, &dya, ya.data(), ya.size()));
+    TRY(launch_upsample(c, dsrc, 0, wc, wc, hc, ddst, 0, w, w, h, dxi, dxa, dyi, dya, 1));
+    CK(c, cudaStreamSynchronize(c->s_comp));
+    CK(c, cudaMemcpy(out, ddst, (size_t)w * h * 8, cudaMemcpyDeviceToHost));
+    return FFB_OK;
+}
+
+// ---- instrumentation ---------------------------------------------------------------------
+int ffb_profile(ffb_ctx* c, int enable) {
+    if (!c) return FFB_E_INVALID;
+    CK(c, cudaStreamSynchronize(c->s_comp));
+    prof_collect(c);
+    c->prof = enable != 0;
+    return FFB_OK;
+}
+int ffb_profile_reset(ffb_ctx* c) {
+    if (!c) return FFB_E_INVALID;
+    CK(c, cudaStreamSynchronize(c->s_comp));
+    prof_collect(c);
+    for (int i = 0; i < FFB_K_COUNT; ++i) { c->k_launches[i] = 0; c->k_ms[i] = 0; c->k_bytes[i] = 0; }
+    return FFB_OK;
+}
+int ffb_kernel_stats(ffb_ctx* c, int kid, int64_t* launches, double* ms, double* bytes) {
+    if (!c || kid < 0 || kid >= FFB_K_COUNT) return FFB_E_INVALID;
+    CK(c, cudaStreamSynchronize(c->s_comp));
+    prof_collect(c);
+    if (launches) *launches = c->k_launches[kid];
+    if (ms) *ms = c->k_ms[kid];
+    if (bytes) *bytes = c->k_bytes[kid];
+    return FFB_OK;
+}
+int64_t ffb_launch_count(const ffb_ctx* c) { return c ? c->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,618 @@
+// ffb_kernels.cuh -- hand-written sm_100a kernels of the frame-pair -> radial-scalar hot path.
+//
+// All kernels are HBM-bound stencils / gathers / reductions in fp32 (fp64 only in reductions);
+// there is no GEMM-shaped work, so no tensor-core path.  Every kernel takes the batch index
+// (frame or pair) in blockIdx.z so that small frames still fill the 148 SMs.
+//
+// Reference stages (F:n = FunscriptFlow.pyw line n; OpenCV = the un-vendored cv2 dependency):
+//   k_pyramid_level   A1a  convertTo + GaussianBlur(REFLECT_101) + resize(INTER_LINEAR)   (inside F:878)
+//   k_polyexp         A1b  FarnebackPolyExp                                                 (inside F:878)
+//   k_upsample_flow   A1e  resize(prevFlow) * 2                                             (inside F:878)
+//   k_flow_iter       A1c+A1d  FarnebackUpdateMatrices + 15x15 box mean + 2x2 solve, fused  (inside F:878)
+//   k_divmag          A3+A4 np.gradient "divergence" argmax + magnitude sum                 F:754-757, F:889-890
+//   k_phase1_finish   A2/A3/A4 finish: centre, value, mean magnitude, cut flag              F:880-894
+//   k_smooth_centers  A5   +-6 centre mean                                                  F:1203-1214
+//   k_radial(+finish) A6   balanced weighted radial projection mean                         F:761-785
+#pragma once
+#include "ffb_common.h"
+
+// ======================================================================================
+// small device helpers
+// ======================================================================================
+__device__ __forceinline__ int ffb_reflect101(int i, int n) {
+    if (n == 1) return 0;
+    const int period = 2 * (n - 1);
+    i %= period;
+    if (i < 0) i += period;
+    return i >= n ? period - i : i;
+}
+__device__ __forceinline__ int ffb_clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+template <class T>
+__device__ __forceinline__ T ffb_warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ unsigned long long ffb_warp_max_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = t > v ? t : v;
+    }
+    return v;
+}
+
+// ======================================================================================
+// K1  pyramid level: u8 frame -> f32 level image
+// ======================================================================================
+struct FfbPyrArgs {
+    const uint8_t* src; size_t src_frame_stride; int src_pitch; int W, H;
+    float* dst; size_t dst_frame_stride; int dp; int w, h;        // strides in floats
+    const int* xi; const float* xa; const int* yi; const float* ya;  // resize tables (device)
+    FfbTaps taps;
+    int RWp;        // smem region row pitch (bytes)
+    int p_off;      // byte offset of the float plane P inside dynamic smem
+};
+
+__device__ __forceinline__ float ffb_blur_u8(const unsigned char* row, int c, const FfbTaps& t) {
+    float s = t.k[0] * (float)row[c];
+    for (int i = 1; i <= t.r; ++i) s += t.k[i] * ((float)row[c - i] + (float)row[c + i]);
+    return s;
+}
+
+template <int TW, int TH>
+__global__ void __launch_bounds__(TW* TH) k_pyramid_level(FfbPyrArgs a) {
+    FFB_DYN_SMEM(unsigned char, smem);
+    unsigned char* reg = smem;
+    float* P = reinterpret_cast<float*>(smem + a.p_off);
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, f = blockIdx.z;
+    const int x_last = min(x0 + TW, a.w) - 1, y_last = min(y0 + TH, a.h) - 1;
+    const int r = a.taps.r;
+    const int sx_lo = a.xi[x0] - r;
+    const int sx_hi = min(a.xi[x_last] + 1, a.W - 1) + r;
+    const int sy_lo = a.yi[y0] - r;
+    const int sy_hi = min(a.yi[y_last] + 1, a.H - 1) + r;
+    const int rw = sx_hi - sx_lo + 1, rh = sy_hi - sy_lo + 1;
+    const uint8_t* src = a.src + (size_t)f * a.src_frame_stride;
+    // stage the source window (border handled here: REFLECT_101, like cv::GaussianBlur's default)
+    for (int i = tid; i < rw * rh; i += TW * TH) {
+        const int ry = i / rw, rx = i - ry * rw;
+        const int sy = ffb_reflect101(sy_lo + ry, a.H), sx = ffb_reflect101(sx_lo + rx, a.W);
+        reg[ry * a.RWp + rx] = src[(size_t)sy * a.src_pitch + sx];
+    }
+    __syncthreads();
+    // pass 1: horizontal blur evaluated only at the two resize taps of each output column, lerped
+    for (int i = tid; i < rh * TW; i += TW * TH) {
+        const int ry = i / TW, ox = i - ry * TW;
+        const int dx = x0 + ox;
+        float v = 0.f;
+        if (dx < a.w) {
+            const int s0 = a.xi[dx];
+            const float al = a.xa[dx];
+            const unsigned char* row = reg + ry * a.RWp;
+            const float b0 = ffb_blur_u8(row, s0 - sx_lo, a.taps);
+            if (al != 0.f) {
+                const float b1 = ffb_blur_u8(row, min(s0 + 1, a.W - 1) - sx_lo, a.taps);
+                v = b0 * (1.f - al) + b1 * al;
+            } else {
+                v = b0;
+            }
+        }
+        P[ry * TW + ox] = v;
+    }
+    __syncthreads();
+    // pass 2: vertical blur at the two resize rows, lerped
+    const int ox = tid % TW, oy = tid / TW;
+    const int dx = x0 + ox, dy = y0 + oy;
+    if (dx < a.w && dy < a.h) {
+        const int s0 = a.yi[dy];
+        const float be = a.ya[dy];
+        const float* col = P + ox;
+        int c = s0 - sy_lo;
+        float b0 = a.taps.k[0] * col[c * TW];
+        for (int i = 1; i <= r; ++i) b0 += a.taps.k[i] * (col[(c - i) * TW] + col[(c + i) * TW]);
+        float v = b0;
+        if (be != 0.f) {
+            c = min(s0 + 1, a.H - 1) - sy_lo;
+            float b1 = a.taps.k[0] * col[c * TW];
+            for (int i = 1; i <= r; ++i) b1 += a.taps.k[i] * (col[(c - i) * TW] + col[(c + i) * TW]);
+            v = b0 * (1.f - be) + b1 * be;
+        }
+        a.dst[(size_t)f * a.dst_frame_stride + (size_t)dy * a.dp + dx] = v;
+    }
+}
+
+// ======================================================================================
+// K2  polynomial expansion: f32 image -> 5 planes (d/dy, d/dx, yy, xx, xy)
+// ======================================================================================
+struct FfbPolyArgs {
+    const float* src; size_t src_frame_stride; int sp; int w, h;  // strides in floats
+    FfbRing dst;            // per frame: 5 planes of plane floats, row pitch rp
+    size_t plane; int rp;
+    FfbPolyConsts c;
+};
+
+template <int TW, int TH>
+__global__ void __launch_bounds__(TW* TH) k_polyexp(FfbPolyArgs a) {
+    constexpr int N = FFB_POLY_N;
+    constexpr int IW = TW + 2 * N, IH = TH + 2 * N;
+    __shared__ float in[IH][IW];
+    __shared__ float vr[3][TH][IW];
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, f = blockIdx.z;
+    const float* src = a.src + (size_t)f * a.src_frame_stride;
+    // replicate border (FarnebackPolyExp clamps rows with max/min and replicates the row buffer)
+    for (int i = tid; i < IW * IH; i += TW * TH) {
+        const int ry = i / IW, rx = i - ry * IW;
+        const int sy = ffb_clampi(y0 - N + ry, 0, a.h - 1), sx = ffb_clampi(x0 - N + rx, 0, a.w - 1);
+        in[ry][rx] = src[(size_t)sy * a.sp + sx];
+    }
+    __syncthreads();
+    // vertical pass: three row sums (g, xg, xxg along y), symmetric pairing as in the CPU code
+    for (int i = tid; i < TH * IW; i += TW * TH) {
+        const int oy = i / IW, cx = i - oy * IW;
+        const float c0 = in[oy + N][cx];
+        float t0 = c0 * a.c.g[0], t1 = 0.f, t2 = 0.f;
+#pragma unroll
+        for (int k = 1; k <= N; ++k) {
+            const float up = in[oy + N - k][cx], dn = in[oy + N + k][cx];
+            const float p = up + dn;
+            t0 += a.c.g[k] * p;
+            t1 += a.c.xg[k] * (dn - up);
+            t2 += a.c.xxg[k] * p;
+        }
+        vr[0][oy][cx] = t0;
+        vr[1][oy][cx] = t1;
+        vr[2][oy][cx] = t2;
+    }
+    __syncthreads();
+    const int ox = tid % TW, oy = tid / TW;
+    const int x = x0 + ox, y = y0 + oy;
+    if (x < a.w && y < a.h) {
+        const float* r0 = &vr[0][oy][ox + N];
+        const float* r1 = &vr[1][oy][ox + N];
+        const float* r2 = &vr[2][oy][ox + N];
+        float b1 = r0[0] * a.c.g[0], b2 = 0.f, b3 = r1[0] * a.c.g[0], b4 = 0.f, b5 = r2[0] * a.c.g[0], b6 = 0.f;
+#pragma unroll
+        for (int k = 1; k <= N; ++k) {
+            const float p = r0[k], m = r0[-k];
+            const float tg = p + m;
+            b1 += tg * a.c.g[k];
+            b4 += tg * a.c.xxg[k];
+            b2 += (p - m) * a.c.xg[k];
+            b3 += (r1[k] + r1[-k]) * a.c.g[k];
+            b6 += (r1[k] - r1[-k]) * a.c.xg[k];
+            b5 += (r2[k] + r2[-k]) * a.c.g[k];
+        }
+        float* dst = reinterpret_cast<float*>(ffb_ring_at(a.dst, f)) + (size_t)y * a.rp + x;
+        dst[0] = b3 * a.c.ig11;
+        dst[a.plane] = b2 * a.c.ig11;
+        dst[2 * a.plane] = b1 * a.c.ig03 + b5 * a.c.ig33;
+        dst[3 * a.plane] = b1 * a.c.ig03 + b4 * a.c.ig33;
+        dst[4 * a.plane] = b6 * a.c.ig55;
+    }
+}
+
+// ======================================================================================
+// A1e  flow up-sampling between levels (bilinear, x2)
+// ======================================================================================
+struct FfbUpArgs {
+    const float2* src; size_t src_stride; int sp; int wc, hc;     // strides in float2
+    float2* dst; size_t dst_stride; int dp; int w, h;
+    const int* xi; const float* xa; const int* yi; const float* ya;
+};
+
+__global__ void __launch_bounds__(256) k_upsample_flow(FfbUpArgs a) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= a.w || y >= a.h) return;
+    const float2* src = a.src + (size_t)blockIdx.z * a.src_stride;
+    const int x0 = a.xi[x], x1 = min(x0 + 1, a.wc - 1);
+    const int y0 = a.yi[y], y1 = min(y0 + 1, a.hc - 1);
+    const float al = a.xa[x], be = a.ya[y];
+    const float2 p00 = src[(size_t)y0 * a.sp + x0], p01 = src[(size_t)y0 * a.sp + x1];
+    const float2 p10 = src[(size_t)y1 * a.sp + x0], p11 = src[(size_t)y1 * a.sp + x1];
+    const float tx = p00.x * (1.f - al) + p01.x * al, ty = p00.y * (1.f - al) + p01.y * al;
+    const float bx = p10.x * (1.f - al) + p11.x * al, by = p10.y * (1.f - al) + p11.y * al;
+    float2 o;
+    o.x = (tx * (1.f - be) + bx * be) * 2.f;
+    o.y = (ty * (1.f - be) + by * be) * 2.f;
+    a.dst[(size_t)blockIdx.z * a.dst_stride + (size_t)y * a.dp + x] = o;
+}
+
+// ======================================================================================
+// A1c  per-pixel matrix update (shared by the fused kernel and the stage hook)
+// ======================================================================================
+__device__ __forceinline__ float ffb_border_w(int d) {   // {0.14, 0.14, 0.4472, 0.4472, 0.4472}, 1 beyond
+    return d < 2 ? 0.14f : (d < 5 ? 0.4472f : 1.f);
+}
+
+// R planes: channel c of pixel (x, y) at R[c * plane + y * rp + x].
+__device__ __forceinline__ void ffb_compute_M(const float* __restrict__ R0, const float* __restrict__ R1,
+                                              size_t plane, int rp, int w, int h, int x, int y,
+                                              float dx, float dy, float m[5]) {
+    float fx = (float)x + dx, fy = (float)y + dy;
+    const float x1f = floorf(fx), y1f = floorf(fy);
+    const int x1 = (int)x1f, y1 = (int)y1f;
+    fx -= x1f;
+    fy -= y1f;
+    const float* q = R0 + (size_t)y * rp + x;
+    const float r00 = __ldg(q), r01 = __ldg(q + plane), r02 = __ldg(q + 2 * plane), r03 = __ldg(q + 3 * plane),
+                r04 = __ldg(q + 4 * plane);
+    float r2, r3, r4, r5, r6;
+    if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
+        const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
+        const float* p = R1 + (size_t)y1 * rp + x1;
+#define FFB_SAMP(c) (a00 * __ldg(p + (c)*plane) + a01 * __ldg(p + (c)*plane + 1) + a10 * __ldg(p + (c)*plane + rp) + a11 * __ldg(p + (c)*plane + rp + 1))
+        r2 = FFB_SAMP(0);
+        r3 = FFB_SAMP(1);
+        r4 = (r02 + FFB_SAMP(2)) * 0.5f;
+        r5 = (r03 + FFB_SAMP(3)) * 0.5f;
+        r6 = (r04 + FFB_SAMP(4)) * 0.25f;
+#undef FFB_SAMP
+    } else {
+        r2 = r3 = 0.f;
+        r4 = r02;
+        r5 = r03;
+        r6 = r04 * 0.5f;
+    }
+    r2 = (r00 - r2) * 0.5f;
+    r3 = (r01 - r3) * 0.5f;
+    r2 += r4 * dy + r6 * dx;
+    r3 += r6 * dy + r5 * dx;
+    if ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10)) {
+        const float s = ffb_border_w(x) * ffb_border_w(w - x - 1) * ffb_border_w(y) * ffb_border_w(h - y - 1);
+        r2 *= s; r3 *= s; r4 *= s; r5 *= s; r6 *= s;
+    }
+    m[0] = r4 * r4 + r6 * r6;
+    m[1] = (r4 + r5) * r6;
+    m[2] = r5 * r5 + r6 * r6;
+    m[3] = r4 * r2 + r6 * r3;
+    m[4] = r6 * r2 + r5 * r3;
+}
+
+struct FfbMatArgs {
+    const float* R0; const float* R1; size_t plane; int rp; int w, h;
+    const float2* flow; int fp;
+    float* M;   // 5 planes, same geometry as R
+};
+__global__ void __launch_bounds__(256) k_update_matrices(FfbMatArgs a) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= a.w || y >= a.h) return;
+    float2 d = make_float2(0.f, 0.f);
+    if (a.flow) d = a.flow[(size_t)y * a.fp + x];
+    float m[5];
+    ffb_compute_M(a.R0, a.R1, a.plane, a.rp, a.w, a.h, x, y, d.x, d.y, m);
+#pragma unroll
+    for (int c = 0; c < 5; ++c) a.M[c * a.plane + (size_t)y * a.rp + x] = m[c];
+}
+
+// ======================================================================================
+// K3  fused flow iteration: matrices -> 15x15 box mean (replicate border) -> 2x2 solve
+// ======================================================================================
+// One CTA owns a strip of SW output columns (plus a 7-column halo on each side: one thread per
+// M column) and marches down a segment of SH rows.  The matrices never touch HBM:
+//   * each thread computes the 5-vector M of its column for U new rows (the R1 gather),
+//   * keeps a Kahan-compensated running sum over the last 15 rows (the column ring of raw M
+//     values lives in shared memory so the row leaving the window can be subtracted),
+//   * publishes its vertical sums to a shared row buffer,
+//   * and a quarter of the threads then form the horizontal 15-sums for 4 adjacent outputs from
+//     five aligned 16-byte shared loads per channel, solve the 2x2 system and store float2 x 4.
+struct FfbIterArgs {
+    FfbRing R;              // frame expansions: pair j uses elements j (prev) and j+1 (next)
+    size_t plane; int rp; int w, h;
+    const float2* fin; size_t fin_stride; int fip;   // flow in (NULL = zero), strides in float2
+    FfbRing fout; int fop;                           // flow out ring (element j), pitch in float2
+    int SW;                 // output columns per strip (multiple of 4, <= NT - 14)
+    int SH;                 // rows per segment
+};
+
+template <int NT, int U>
+__host__ __device__ constexpr size_t ffb_flow_iter_smem() { return sizeof(float) * (2 * U * 5 * (NT + 4) + FFB_WIN * 5 * NT); }
+
+template <int NT, int U>
+__global__ void __launch_bounds__(NT) k_flow_iter(FfbIterArgs a) {
+    constexpr int HP = NT + 4;
+    // dynamic shared memory (exceeds the 48 KB static limit): hrow first (16-byte aligned), then ring
+    FFB_DYN_SMEM(float, smem_f);
+    typedef float (*HrowT)[U][5][HP];
+    typedef float (*RingT)[5][NT];
+    HrowT hrow = reinterpret_cast<HrowT>(smem_f);                       // [2][U][5][HP]
+    RingT ring = reinterpret_cast<RingT>(smem_f + 2 * U * 5 * HP);      // [FFB_WIN][5][NT]
+    const int tid = threadIdx.x;
+    const int pair = blockIdx.z;
+    const float* R0 = reinterpret_cast<const float*>(ffb_ring_at(a.R, pair));
+    const float* R1 = reinterpret_cast<const float*>(ffb_ring_at(a.R, pair + 1));
+    const float2* fin = a.fin ? a.fin + (size_t)pair * a.fin_stride : nullptr;
+    float2* fout = reinterpret_cast<float2*>(ffb_ring_at(a.fout, pair));
+    const int w = a.w, h = a.h;
+    const int xo0 = blockIdx.x * a.SW;
+    const int xc = ffb_clampi(xo0 - FFB_WIN_R + tid, 0, w - 1);
+    const int y0 = blockIdx.y * a.SH;
+    const int y1 = min(y0 + a.SH, h);
+    const int nfeed = (y1 - y0) + 2 * FFB_WIN_R;
+    const int nsteps = (nfeed + U - 1) / U;
+    const int groups = a.SW >> 2;
+
+#pragma unroll
+    for (int s = 0; s < FFB_WIN; ++s)
+#pragma unroll
+        for (int c = 0; c < 5; ++c) ring[s][c][tid] = 0.f;
+    if (tid < 4) {
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int c = 0; c < 5; ++c) hrow[b][u][c][NT + tid] = 0.f;
+    }
+    float vs[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, comp[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    int slot = 0;
+
+    for (int s = 0; s < nsteps; ++s) {
+        const int buf = s & 1;
+        // ---- gather phase: U rows of matrices for this thread's column
+        float m[U][5];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = s * U + u;
+            if (i < nfeed) {
+                const int yc = ffb_clampi(y0 - FFB_WIN_R + i, 0, h - 1);
+                float2 d = make_float2(0.f, 0.f);
+                if (fin) d = __ldg(fin + (size_t)yc * a.fip + xc);
+                ffb_compute_M(R0, R1, a.plane, a.rp, w, h, xc, yc, d.x, d.y, m[u]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 5; ++c) m[u][c] = 0.f;
+            }
+        }
+        // ---- vertical running sums (Kahan-compensated add of  new - leaving)
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = s * U + u;
+            if (i < nfeed) {
+#pragma unroll
+                for (int c = 0; c < 5; ++c) {
+                    const float old = ring[slot][c][tid];
+                    ring[slot][c][tid] = m[u][c];
+                    const float yk = (m[u][c] - old) - comp[c];
+                    const float t = vs[c] + yk;
+                    comp[c] = (t - vs[c]) - yk;
+                    vs[c] = t;
+                }
+                slot = slot + 1 == FFB_WIN ? 0 : slot + 1;
+            }
+#pragma unroll
+            for (int c = 0; c < 5; ++c) hrow[buf][u][c][tid] = vs[c];
+        }
+        __syncthreads();
+        // ---- horizontal sums + solve for 4 adjacent outputs
+        if (tid < U * groups) {
+            const int u = tid / groups, g = tid - u * groups;
+            const int i = s * U + u;
+            const int x = xo0 + 4 * g;
+            if (i >= 2 * FFB_WIN_R && i < nfeed && x < w) {
+                const int yo = y0 + i - 2 * FFB_WIN_R;
+                float sum[5][4];
+#pragma unroll
+                for (int c = 0; c < 5; ++c) {
+                    const float4* hp = reinterpret_cast<const float4*>(&hrow[buf][u][c][4 * g]);
+                    const float4 q0 = hp[0], q1 = hp[1], q2 = hp[2], q3 = hp[3], q4 = hp[4];
+                    // window of output 0 = elements 0..14; each next output drops one, adds one
+                    const float mid = ((q0.w + q1.x) + (q1.y + q1.z)) + ((q1.w + q2.x) + (q2.y + q2.z)) +
+                                      ((q2.w + q3.x) + (q3.y + q3.z));          // elements 3..14
+                    sum[c][0] = mid + ((q0.x + q0.y) + q0.z);
+                    sum[c][1] = mid + ((q0.y + q0.z) + q3.w);
+                    sum[c][2] = mid + ((q0.z + q3.w) + q4.x);
+                    sum[c][3] = mid + ((q3.w + q4.x) + q4.y);
+                }
+                float2 o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float sc = 1.f / (float)(FFB_WIN * FFB_WIN);
+                    const float g11 = sum[0][j] * sc, g12 = sum[1][j] * sc, g22 = sum[2][j] * sc;
+                    const float h1 = sum[3][j] * sc, h2 = sum[4][j] * sc;
+                    // det = g11*g22 - g12*g12 with an exact-product correction (Kahan's ad-bc)
+                    const float wq = g12 * g12;
+                    const float e = __fmaf_rn(-g12, g12, wq);
+                    const float fd = __fmaf_rn(g11, g22, -wq);
+                    const float idet = 1.f / ((fd + e) + 1e-3f);
+                    o[j].x = (g11 * h2 - g12 * h1) * idet;
+                    o[j].y = (g22 * h1 - g12 * h2) * idet;
+                }
+                float2* dst = fout + (size_t)yo * a.fop + x;
+                if (x + 3 < w) {
+                    reinterpret_cast<float4*>(dst)[0] = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
+                    reinterpret_cast<float4*>(dst)[1] = make_float4(o[2].x, o[2].y, o[3].x, o[3].y);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (x + j < w) dst[j] = o[j];
+                }
+            }
+        }
+        // hrow is double-buffered: the barrier of the next step orders these reads before the
+        // writes of step s+2 into the same buffer.
+    }
+}
+
+// ======================================================================================
+// K4  swapped-axis "divergence" argmax + magnitude sum   (A3 + A4)
+// ======================================================================================
+struct FfbDivArgs {
+    FfbRing flow; int fp; int w, h;     // pitch in float2
+    int rows_per_block;
+    unsigned long long* pkey;           // [pairs][gridDim.x]
+    double* psum;                       // [pairs][gridDim.x]
+};
+
+__global__ void __launch_bounds__(256) k_divmag(FfbDivArgs a) {
+    __shared__ unsigned long long skey[8];
+    __shared__ double ssum[8];
+    const int pair = blockIdx.z;
+    const float2* F = reinterpret_cast<const float2*>(ffb_ring_at(a.flow, pair));
+    const int w = a.w, h = a.h, fp = a.fp;
+    const int ylo = blockIdx.x * a.rows_per_block, yhi = min(ylo + a.rows_per_block, h);
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    unsigned long long best = 0ull;
+    double msum = 0.0;
+    for (int y = ylo + ty; y < yhi; y += 4) {
+        const float2* row = F + (size_t)y * fp;
+        const float2* up = F + (size_t)(y > 0 ? y - 1 : 0) * fp;
+        const float2* dn = F + (size_t)(y < h - 1 ? y + 1 : h - 1) * fp;
+        const float ysc = (y > 0 && y < h - 1) ? 0.5f : 1.f;
+        for (int x = tx; x < w; x += 64) {
+            const float2 c = __ldg(row + x);
+            const float ua = __ldg(up + x).x, ub = __ldg(dn + x).x;
+            const float vl = __ldg(row + (x > 0 ? x - 1 : 0)).y, vr = __ldg(row + (x < w - 1 ? x + 1 : w - 1)).y;
+            const float xsc = (x > 0 && x < w - 1) ? 0.5f : 1.f;
+            // np.gradient: (f[i+1]-f[i-1])/2 inside, one-sided first differences at the ends
+            const float gu = __fmul_rn(__fsub_rn(ub, ua), ysc);
+            const float gv = __fmul_rn(__fsub_rn(vr, vl), xsc);
+            const float dv = __fadd_rn(gu, gv);
+            const unsigned long long key = ((unsigned long long)__float_as_uint(fabsf(dv)) << 32) |
+                                           (unsigned long long)(0xFFFFFFFFu - (unsigned)(y * w + x));
+            best = key > best ? key : best;
+            msum += (double)sqrtf(__fmaf_rn(c.x, c.x, __fmul_rn(c.y, c.y)));
+        }
+    }
+    best = ffb_warp_max_u64(best);
+    msum = ffb_warp_sum(msum);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { skey[warp] = best; ssum[warp] = msum; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long b = skey[0];
+        double s = ssum[0];
+        for (int i = 1; i < 8; ++i) { b = skey[i] > b ? skey[i] : b; s += ssum[i]; }
+        a.pkey[(size_t)pair * gridDim.x + blockIdx.x] = b;
+        a.psum[(size_t)pair * gridDim.x + blockIdx.x] = s;
+    }
+}
+
+struct FfbP1Args {
+    FfbRing flow; int fp; int w, h;
+    const unsigned long long* pkey; const double* psum; int nblk;
+    int pov; float cut_threshold;
+    int out0;                 // index of the batch's first pair inside the bracket arrays
+    int* cx; int* cy; float* val; float* mean_mag; unsigned char* cut;
+};
+
+__global__ void __launch_bounds__(32) k_phase1_finish(FfbP1Args a) {
+    const int pair = blockIdx.x;
+    const int lane = threadIdx.x;
+    unsigned long long best = 0ull;
+    double s = 0.0;
+    for (int i = lane; i < a.nblk; i += 32) {
+        const unsigned long long k = a.pkey[(size_t)pair * a.nblk + i];
+        best = k > best ? k : best;
+        s += a.psum[(size_t)pair * a.nblk + i];
+    }
+    best = ffb_warp_max_u64(best);
+    s = ffb_warp_sum(s);
+    if (lane == 0) {
+        const int w = a.w, h = a.h;
+        const int o = a.out0 + pair;
+        const float mm = (float)(s / ((double)w * (double)h));
+        a.mean_mag[o] = mm;
+        a.cut[o] = mm > a.cut_threshold ? 1 : 0;
+        if (a.pov) {   // F:880-882
+            a.cx[o] = w / 2;
+            a.cy[o] = h - 1;
+            a.val[o] = 0.f;
+        } else {
+            const unsigned idx = 0xFFFFFFFFu - (unsigned)(best & 0xFFFFFFFFull);
+            const int y = (int)(idx / (unsigned)w), x = (int)(idx - (unsigned)y * (unsigned)w);
+            const float2* F = reinterpret_cast<const float2*>(ffb_ring_at(a.flow, pair));
+            const float ua = F[(size_t)(y > 0 ? y - 1 : 0) * a.fp + x].x;
+            const float ub = F[(size_t)(y < h - 1 ? y + 1 : h - 1) * a.fp + x].x;
+            const float vl = F[(size_t)y * a.fp + (x > 0 ? x - 1 : 0)].y;
+            const float vr = F[(size_t)y * a.fp + (x < w - 1 ? x + 1 : w - 1)].y;
+            const float gu = __fmul_rn(__fsub_rn(ub, ua), (y > 0 && y < h - 1) ? 0.5f : 1.f);
+            const float gv = __fmul_rn(__fsub_rn(vr, vl), (x > 0 && x < w - 1) ? 0.5f : 1.f);
+            a.cx[o] = x;
+            a.cy[o] = y;
+            a.val[o] = __fadd_rn(gu, gv);
+        }
+    }
+}
+
+// ======================================================================================
+// A5  +-6 centre mean (F:1203-1214)
+// ======================================================================================
+__global__ void __launch_bounds__(128) k_smooth_centers(const int* cx, const int* cy, int n, int j0, int j1,
+                                                        double* centers /* [n][2] */) {
+    const int j = j0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= j1) return;
+    const int lo = max(0, j - 6), hi = min(n, j + 7);
+    long long sx = 0, sy = 0;
+    for (int i = lo; i < hi; ++i) { sx += cx[i]; sy += cy[i]; }
+    centers[2 * j] = (double)sx / (double)(hi - lo);
+    centers[2 * j + 1] = (double)sy / (double)(hi - lo);
+}
+
+// ======================================================================================
+// K5  balanced weighted radial projection mean   (A6)
+// ======================================================================================
+// result = 1/(HW) * sum_y wy(y) * [ sum_x u*wx(x)*(x-cx) + (y-cy) * sum_x v*wx(x) ]
+// with wx = (W-x)/W for x > cx else x/W (same for y); POV mode: wx = wy = 1.
+struct FfbRadArgs {
+    FfbRing flow; int fp; int w, h;
+    int rows_per_block;
+    const double* centers;       // [bracket pairs][2]
+    const unsigned char* cut;    // [bracket pairs]
+    int out0;                    // bracket index of ring element 0 of this launch
+    int pov;
+    double* partial;             // [pairs][gridDim.y * gridDim.x]
+};
+
+__global__ void __launch_bounds__(256) k_radial(FfbRadArgs a) {
+    __shared__ double ssum[8];
+    const int pair = blockIdx.z;
+    const int o = a.out0 + pair;
+    const int nblk = gridDim.x * gridDim.y;
+    const int bid = blockIdx.y * gridDim.x + blockIdx.x;
+    if (a.cut[o]) {   // F:766-767: a cut contributes exactly 0.0 and its flow is never read
+        if (threadIdx.x == 0) a.partial[(size_t)pair * nblk + bid] = 0.0;
+        return;
+    }
+    const float2* F = reinterpret_cast<const float2*>(ffb_ring_at(a.flow, pair));
+    const double cx = a.centers[2 * o], cy = a.centers[2 * o + 1];
+    const int w = a.w, h = a.h;
+    const int x = blockIdx.x * 256 + threadIdx.x;
+    const int ylo = blockIdx.y * a.rows_per_block, yhi = min(ylo + a.rows_per_block, h);
+    double acc = 0.0;
+    if (x < w) {
+        const double wxd = a.pov ? 1.0 : (((double)x > cx) ? (double)(w - x) / (double)w : (double)x / (double)w);
+        const float wx = (float)wxd;
+        const float ax = (float)(wxd * ((double)x - cx));
+        for (int y = ylo; y < yhi; ++y) {
+            const float2 f = __ldg(F + (size_t)y * a.fp + x);
+            const double wy = a.pov ? 1.0 : (((double)y > cy) ? (double)(h - y) / (double)h : (double)y / (double)h);
+            const float dyf = (float)((double)y - cy);
+            const float t = __fmaf_rn(f.x, ax, __fmul_rn(__fmul_rn(f.y, wx), dyf));
+            acc += (double)t * wy;
+        }
+    }
+    acc = ffb_warp_sum(acc);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) ssum[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < 8; ++i) s += ssum[i];
+        a.partial[(size_t)pair * nblk + bid] = s;
+    }
+}
+
+__global__ void __launch_bounds__(32) k_radial_finish(const double* partial, int nblk, int w, int h, int out0,
+                                                      double* scalar) {
+    const int pair = blockIdx.x;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nblk; i += 32) s += partial[(size_t)pair * nblk + i];
+    s = ffb_warp_sum(s);
+    if (threadIdx.x == 0) scalar[out0 + pair] = s / ((double)w * (double)h);
+}

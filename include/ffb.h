@@ -1,0 +1,148 @@
+/*
+ * ffb.h -- C ABI of the B200-native Funscript-Flow motion hot path
+ *          (grayscale frame pair -> per-pair radial expansion scalar).
+ *
+ * The reference (ConwayBeyond/Funscript-Flow, FunscriptFlow.pyw; "F:n" = line n of that file) has
+ * no FFI of its own: its seam is Python-level (config["backend"], F:854-873) and the arithmetic
+ * lives in cv2 / NumPy calls.  Each entry point below names the reference interface it replaces,
+ * so a maintainer can bind it with ctypes (see INTEGRATION.md for the stub).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++ / torch types.
+ *   - every function returns 0 on success or a negative FFB_E_* code; ffb_last_error() gives text.
+ *   - a context is bound to one CUDA device and is NOT thread-safe (one per host thread / GPU).
+ *   - host buffers are borrowed, never retained past the documented point, never written unless
+ *     they are outputs.  All device memory, streams and pinned staging belong to the context.
+ *   - there is no CPU fallback: without a usable CUDA device ffb_create() fails.
+ *   - image layout: uint8 gray, row-major, `pitch` bytes per row, `frame_stride` bytes per frame.
+ *   - flow layout: float32 [H][W][2] interleaved, channel 0 = x displacement, 1 = y displacement
+ *     (exactly cv2.calcOpticalFlowFarneback's output, F:878-879).
+ */
+#ifndef FFB_H_
+#define FFB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FFB_VERSION 100
+
+#define FFB_OK             0
+#define FFB_E_INVALID     -1   /* bad argument / call out of sequence                     */
+#define FFB_E_CUDA        -2   /* CUDA runtime error (text in ffb_last_error)              */
+#define FFB_E_NOMEM       -3   /* host or device allocation failed                         */
+#define FFB_E_NODEVICE    -4   /* no CUDA device: there is no CPU fallback                 */
+#define FFB_E_RANGE       -5   /* index outside what is resident (e.g. evicted flow field) */
+
+typedef struct ffb_ctx ffb_ctx;
+
+/* ---- library / device ------------------------------------------------------------------ */
+int  ffb_version(void);
+/* replaces get_available_backends()["CUDA"] (F:32-63): number of usable CUDA devices. */
+int  ffb_device_count(int* n_devices);
+const char* ffb_last_error(const ffb_ctx* ctx /* NULL = last error of ffb_create */);
+
+int  ffb_create(int device, ffb_ctx** out_ctx);
+void ffb_destroy(ffb_ctx* ctx);
+
+/* Pinned host memory for frame buffers (so ffb_bracket_push can DMA straight out of them). */
+int  ffb_host_alloc(void** ptr, size_t bytes);
+int  ffb_host_free(void* ptr);
+
+/* ---- geometry ---------------------------------------------------------------------------
+ * (Re)allocate device buffers for width x height frames.
+ *   batch_frames       frames expanded per launch group (>= 1); pairs of a batch share launches
+ *   max_bracket_pairs  upper bound on pairs between bracket_begin and bracket_finish
+ * Farneback parameters are fixed to the reference's call (F:878-879):
+ *   pyr_scale 0.5, levels 3, winsize 15, iterations 3, poly_n 5, poly_sigma 1.2, flags 0. */
+int  ffb_configure(ffb_ctx* ctx, int width, int height, int batch_frames, int max_bracket_pairs);
+
+/* ---- streaming bracket API (replaces the bracket loop body F:1188-1242) ------------------
+ * A bracket is a run of consecutive sampled frames; pairs never span brackets (F:1150-1153,
+ * 1188) and the +-6 centre window is truncated at bracket ends (F:1203-1214).
+ *
+ *   ffb_bracket_begin(ctx, pov_mode, cut_threshold)
+ *   ffb_bracket_push(ctx, frames, n, pitch, frame_stride)      any number of times
+ *   ffb_bracket_finish(ctx, &n_pairs, outputs...)
+ *
+ * push: `frames` may be pageable host memory (copied through the context's pinned double
+ * buffer), pinned host memory (DMA'd directly; keep it valid until ffb_bracket_finish or
+ * ffb_sync) or device memory (used in place; same lifetime rule).  Uploads run with
+ * cudaMemcpyAsync on a side stream, double-buffered against compute.
+ *
+ * finish outputs (each may be NULL), one entry per pair j = (frame j, frame j+1):
+ *   scalar[j]    radial_motion_weighted(flow_j, smoothed_centre_j, cut_j, pov_mode)  F:761-785
+ *   cut[j]       mean(|flow_j|) > cut_threshold                                        F:889-894
+ *   cx, cy, val  max_divergence(flow_j) (or the POV shortcut F:880-882)               F:748-758
+ *   mean_mag[j]  float32 mean flow magnitude                                           F:890
+ *   centers[2j], centers[2j+1]   the +-6 smoothed centre (x, y) as float64            F:1201-1214 */
+int  ffb_bracket_begin(ffb_ctx* ctx, int pov_mode, double cut_threshold);
+int  ffb_bracket_push(ffb_ctx* ctx, const uint8_t* frames, int n_frames, size_t pitch, size_t frame_stride);
+int  ffb_bracket_finish(ffb_ctx* ctx, int* n_pairs, double* scalar, uint8_t* cut, int32_t* cx, int32_t* cy,
+                        float* val, float* mean_mag, double* centers);
+/* Block until all uploads issued so far have left the caller's buffers. */
+int  ffb_sync(ffb_ctx* ctx);
+/* Copy the final flow field of pair `pair` of the current / last bracket to host (test hook and
+ * the "flow" entry of the drop-in dict, F:899).  Only the most recent ring of pairs is resident
+ * (FFB_E_RANGE otherwise); ffb_flow_ring_size() tells how many. */
+int  ffb_bracket_get_flow(ffb_ctx* ctx, int pair, float* flow_hw2);
+int  ffb_flow_ring_size(const ffb_ctx* ctx);
+
+/* ---- per-call functions on host arrays (drop-ins for the module-level functions) ----------
+ * ffb_farneback   == cv2.calcOpticalFlowFarneback(p0, p1, None, .5, 3, 15, 3, 5, 1.2, 0) F:878
+ * ffb_max_divergence     == max_divergence(flow)                                         F:748
+ * ffb_mean_magnitude     == np.mean(cv2.cartToPolar(u, v)[0])                            F:889-890
+ * ffb_radial_motion      == radial_motion_weighted(flow, (cx, cy), is_cut, pov_mode)     F:761 */
+int  ffb_farneback(ffb_ctx* ctx, const uint8_t* prev, const uint8_t* next, int width, int height,
+                   size_t pitch, float* flow_hw2);
+int  ffb_max_divergence(ffb_ctx* ctx, const float* flow_hw2, int width, int height,
+                        int32_t* x, int32_t* y, float* val);
+int  ffb_mean_magnitude(ffb_ctx* ctx, const float* flow_hw2, int width, int height, float* mean_mag);
+int  ffb_radial_motion(ffb_ctx* ctx, const float* flow_hw2, int width, int height,
+                       double cx, double cy, int is_cut, int pov_mode, double* out);
+
+/* ---- per-stage hooks (each runs exactly the production kernel of that stage) --------------
+ * Level geometry of the Farneback pyramid for a frame size (coarsest level first):
+ * fills up to 4 entries of w[], h[], ksize[], sigma[]; returns the level count in *n_levels. */
+int  ffb_level_plan(int width, int height, int* n_levels, int* w, int* h, int* ksize, double* sigma);
+/* A1a: u8 frame -> float32 level image (GaussianBlur REFLECT_101 at full res + bilinear resize). */
+int  ffb_stage_pyramid(ffb_ctx* ctx, const uint8_t* img, int width, int height, size_t pitch,
+                       int level_k, float* out_hw);
+/* A1b: float32 image -> float32 [5][h][w] planes (d/dy, d/dx, yy, xx, xy). */
+int  ffb_stage_polyexp(ffb_ctx* ctx, const float* img, int w, int h, float* out_5hw);
+/* A1c: R0, R1 ([5][h][w] planes), flow [h][w][2] -> M [5][h][w] planes (G11,G12,G22,h1,h2). */
+int  ffb_stage_update_matrices(ffb_ctx* ctx, const float* R0, const float* R1, const float* flow,
+                               int w, int h, float* out_5hw);
+/* A1c+A1d fused (the production flow iteration): R0, R1, flow_in -> flow_out [h][w][2].
+ * flow_in may be NULL (zero initial flow). */
+int  ffb_stage_flow_iter(ffb_ctx* ctx, const float* R0, const float* R1, const float* flow_in,
+                         int w, int h, float* flow_out);
+/* A1e: coarse flow [hc][wc][2] -> [h][w][2], bilinear, x2. */
+int  ffb_stage_upsample_flow(ffb_ctx* ctx, const float* flow_c, int wc, int hc, int w, int h, float* out);
+
+/* ---- instrumentation ----------------------------------------------------------------------
+ * Kernel ids for ffb_kernel_stats. */
+#define FFB_K_PYRAMID   0
+#define FFB_K_POLYEXP   1
+#define FFB_K_UPSAMPLE  2
+#define FFB_K_FLOW_ITER 3
+#define FFB_K_DIVMAG    4
+#define FFB_K_RADIAL    5
+#define FFB_K_SMALL     6   /* finish / centre-smoothing kernels */
+#define FFB_K_COUNT     7
+/* When enabled, every launch of the kernels above is bracketed by CUDA events on the compute
+ * stream; ffb_kernel_stats returns launches, summed device milliseconds and the algorithmic
+ * bytes those launches moved (DESIGN.md section "bytes per unit") since the last reset. */
+int  ffb_profile(ffb_ctx* ctx, int enable);
+int  ffb_profile_reset(ffb_ctx* ctx);
+int  ffb_kernel_stats(ffb_ctx* ctx, int kernel_id, int64_t* launches, double* ms, double* alg_bytes);
+int64_t ffb_launch_count(const ffb_ctx* ctx);   /* kernels launched by this context so far */
+const char* ffb_kernel_name(int kernel_id);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FFB_H_ */
