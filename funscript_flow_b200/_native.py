@@ -69,6 +69,8 @@ def load(path: Optional[str] = None) -> C.CDLL:
         "ffb_kernel_stats": (i32, [vp, i32, C.POINTER(C.c_int64), f64p, f64p]),
         "ffb_launch_count": (C.c_int64, [vp]),
         "ffb_kernel_name": (C.c_char_p, [i32]),
+        "ffb_timer_mark": (i32, [vp, i32]),
+        "ffb_timer_elapsed": (i32, [vp, i32, i32, f64p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)   # AttributeError here = the .so does not export a declared symbol
@@ -316,6 +318,14 @@ class FlowContext:
             self._ck(self._lib.ffb_kernel_stats(self._h, kid, C.byref(n), C.byref(ms), C.byref(by)))
             out[name] = dict(launches=int(n.value), ms=float(ms.value), alg_bytes=float(by.value))
         return out
+
+    def timer_mark(self, slot: int):
+        self._ck(self._lib.ffb_timer_mark(self._h, int(slot)))
+
+    def timer_elapsed_ms(self, slot_from: int, slot_to: int) -> float:
+        ms = C.c_double()
+        self._ck(self._lib.ffb_timer_elapsed(self._h, int(slot_from), int(slot_to), C.byref(ms)))
+        return float(ms.value)
 
     @property
     def launch_count(self) -> int:

@@ -1,0 +1,162 @@
+"""Drop-in processing functions with the reference's names, signatures and return shapes
+(FunscriptFlow.pyw, "F:n" = line n), backed by the sm_100a kernels through the C ABI.
+
+    precompute_flow_info(p0, p1, config)            F:843-907   (8-key dict, F:898-907)
+    precompute_flow_info_gpu(p0, p1, cut_threshold) F:982-1017  (the slot this build fills)
+    precompute_wrapper(p, params)                   F:1019-1021
+    max_divergence(flow)                            F:748-758
+    radial_motion_weighted(flow, center, is_cut, pov_mode=False)   F:761-785
+    get_available_backends()                        F:32-63
+
+plus the batched entry the GPU runner uses, because per-pair calls from forked pool workers
+(F:1190-1191) cannot drive a GPU:
+
+    process_bracket(frames, params) -> dict of per-pair arrays   (F:1188-1242 in one call)
+
+There is no CPU path here: every function raises if libffb.so or a CUDA device is missing.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+
+from . import _native
+
+DEFAULT_CUT_THRESHOLD = 7          # F:876
+DEFAULT_BATCH_FRAMES = 16
+
+_contexts: Dict[int, _native.FlowContext] = {}
+
+
+def default_device() -> int:
+    for key in ("FFB_DEVICE", "LOCAL_RANK"):
+        if os.environ.get(key, "") != "":
+            return int(os.environ[key])
+    return 0
+
+
+def get_context(device: Optional[int] = None) -> _native.FlowContext:
+    """Process-wide context per device (created lazily; raises without a GPU)."""
+    dev = default_device() if device is None else int(device)
+    ctx = _contexts.get(dev)
+    if ctx is None:
+        ctx = _native.FlowContext(dev)
+        _contexts[dev] = ctx
+    return ctx
+
+
+def set_context(ctx: _native.FlowContext, device: int = 0) -> None:
+    """Install an externally created context (tests use this to inject the emulated library)."""
+    _contexts[int(device)] = ctx
+
+
+def get_available_backends() -> Dict[str, bool]:
+    """Shape of F:32-63's result.  Only the CUDA entry can be True: this build ships no CPU,
+    OpenCL or DIS path."""
+    try:
+        n = _native.device_count()
+    except Exception:
+        n = 0
+    return {"CPU": False, "CUDA": n > 0, "OpenCL": False, "DNN": False}
+
+
+def _as_frames(frames) -> np.ndarray:
+    if isinstance(frames, np.ndarray) and frames.ndim == 3:
+        arr = frames
+    else:
+        arr = np.stack([np.asarray(f) for f in frames])
+    if arr.dtype != np.uint8:
+        raise TypeError("frames must be uint8 grayscale")
+    return np.ascontiguousarray(arr)
+
+
+def process_bracket(frames, params: Optional[Dict] = None, *, ctx: Optional[_native.FlowContext] = None,
+                    batch_frames: int = DEFAULT_BATCH_FRAMES, return_flows: bool = False) -> Dict:
+    """One bracket of N consecutive sampled frames -> N-1 pairs (F:1188-1242 as one GPU pass).
+
+    Returns a dict with per-pair arrays: scalar (f64), cut (bool), cx / cy (int32), val (f32),
+    mean_mag (f32), centers (f64 [N-1, 2], the +-6 smoothed centre) and n_pairs.  With
+    return_flows=True also `flows` (f32 [k, H, W, 2]) for the last k <= ring pairs (tests).
+    """
+    params = params or {}
+    ctx = ctx or get_context()
+    arr = _as_frames(frames)
+    n, h, w = arr.shape
+    ctx.configure(w, h, max(1, min(batch_frames, n)), max(n - 1, 1))
+    ctx.bracket_begin(bool(params.get("pov_mode", False)), float(params.get("cut_threshold", DEFAULT_CUT_THRESHOLD)))
+    ctx.bracket_push(arr)
+    res = ctx.bracket_finish()
+    if return_flows:
+        k = res["n_pairs"]
+        first = max(0, k - ctx.flow_ring_size)
+        res["flow_first"] = first
+        res["flows"] = np.stack([ctx.get_flow(p) for p in range(first, k)]) if k else np.empty((0, h, w, 2), np.float32)
+    return res
+
+
+def precompute_flow_info(p0: np.ndarray, p1: np.ndarray, config: Dict) -> Dict:
+    """F:843-907.  `config["backend"]` is ignored (there is one backend); `pov_mode` and the
+    hidden `cut_threshold` key are honoured like the CPU branch (F:876-894)."""
+    ctx = get_context()
+    p0 = np.ascontiguousarray(p0, dtype=np.uint8)
+    p1 = np.ascontiguousarray(p1, dtype=np.uint8)
+    if p0.shape != p1.shape or p0.ndim != 2:
+        raise ValueError("p0 and p1 must be equal-sized 2-D uint8 arrays")
+    h, w = p0.shape
+    pov = bool(config.get("pov_mode"))
+    ctx.configure(w, h, 2, 64)
+    ctx.bracket_begin(pov, float(config.get("cut_threshold", DEFAULT_CUT_THRESHOLD)))
+    ctx.bracket_push(p0)
+    ctx.bracket_push(p1)
+    r = ctx.bracket_finish()
+    flow = ctx.get_flow(0)
+    if pov:   # F:882: plain Python ints and the int 0
+        pos_center, val = (w // 2, h - 1), 0
+    else:     # F:757-758: NumPy integer / float32 scalars
+        pos_center, val = (np.int64(r["cx"][0]), np.int64(r["cy"][0])), np.float32(r["val"][0])
+    return {
+        "flow": flow,
+        "pos_center": pos_center,
+        "neg_center": pos_center,
+        "val_pos": val,
+        "val_neg": val,
+        "cut": bool(r["cut"][0]),
+        "cut_center": pos_center[0],
+        "mean_mag": np.float32(r["mean_mag"][0]),
+    }
+
+
+def precompute_flow_info_gpu(p0: np.ndarray, p1: np.ndarray, cut_threshold) -> Dict:
+    """F:982-1017: same dict, threshold passed positionally, no config (hence no POV mode)."""
+    return precompute_flow_info(p0, p1, {"cut_threshold": cut_threshold})
+
+
+def precompute_wrapper(p, params):
+    """F:1019-1021."""
+    return precompute_flow_info(p[0], p[1], params)
+
+
+def max_divergence(flow: np.ndarray):
+    """F:748-758: (x, y, value) of the first maximum of |d flow[...,0]/d row + d flow[...,1]/d col|."""
+    x, y, v = get_context().max_divergence(flow)
+    return np.int64(x), np.int64(y), v
+
+
+def radial_motion_weighted(flow: np.ndarray, center, is_cut, pov_mode: bool = False):
+    """F:761-785."""
+    if is_cut:
+        return 0.0
+    return np.float64(get_context().radial_motion(flow, center, False, bool(pov_mode)))
+
+
+def smooth_centers(centers: Sequence, radius: int = 6) -> np.ndarray:
+    """F:1201-1214 on the host (the runner does this on the device; kept for API parity)."""
+    c = np.asarray(centers, dtype=np.int64).reshape(-1, 2)
+    n = len(c)
+    csum = np.concatenate([np.zeros((1, 2), np.int64), np.cumsum(c, axis=0)])
+    j = np.arange(n)
+    lo = np.maximum(j - radius, 0)
+    hi = np.minimum(j + radius + 1, n)
+    return (csum[hi] - csum[lo]) / (hi - lo)[:, None].astype(np.float64)

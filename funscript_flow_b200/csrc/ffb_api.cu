@@ -214,6 +214,7 @@ struct ffb_ctx {
     int64_t k_launches[FFB_K_COUNT] = {0};
     double k_ms[FFB_K_COUNT] = {0}, k_bytes[FFB_K_COUNT] = {0};
     int64_t launches = 0;
+    cudaEvent_t timers[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -732,6 +733,7 @@ void ffb_destroy(ffb_ctx* c) {
     cudaStreamSynchronize(c->s_copy);
     prof_collect(c);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->timers) if (e) cudaEventDestroy(e);
     free_geometry(c);
     for (int b = 0; b < 2; ++b) { cudaEventDestroy(c->ev_h2d[b]); cudaEventDestroy(c->ev_expand[b]); }
     cudaStreamDestroy(c->s_comp);
@@ -1062,5 +1064,20 @@ int ffb_kernel_stats(ffb_ctx* c, int kid, int64_t* launches, double* ms, double*
     return FFB_OK;
 }
 int64_t ffb_launch_count(const ffb_ctx* c) { return c ? c->launches : 0; }
+
+int ffb_timer_mark(ffb_ctx* c, int slot) {
+    if (!c || slot < 0 || slot >= 8) return FFB_E_INVALID;
+    if (!c->timers[slot]) CK(c, cudaEventCreate(&c->timers[slot]));
+    CK(c, cudaEventRecord(c->timers[slot], c->s_comp));
+    return FFB_OK;
+}
+int ffb_timer_elapsed(ffb_ctx* c, int a, int b, double* ms) {
+    if (!c || !ms || a < 0 || a >= 8 || b < 0 || b >= 8 || !c->timers[a] || !c->timers[b]) return FFB_E_INVALID;
+    CK(c, cudaEventSynchronize(c->timers[b]));
+    float f = 0.f;
+    CK(c, cudaEventElapsedTime(&f, c->timers[a], c->timers[b]));
+    *ms = f;
+    return FFB_OK;
+}
 
 }  // extern "C"

@@ -1,0 +1,162 @@
+"""GPU batch runner with the reference's orchestration contracts.
+
+    process_video(video_path, params, log_func, progress_callback=None, cancel_flag=None,
+                  preview_callback=None) -> error_occurred        (F:1094-1404)
+    run_headless(input_path, settings)                              (F:2606-2638)
+    process_frames(frames, fps, params, ...) -> actions             (same pipeline on in-memory frames)
+
+Semantics kept from the reference: brackets of `batch_size` sampled frames are independent (no pair
+spans two brackets, a trailing 1-frame bracket is dropped, the +-6 centre window is truncated at
+bracket ends: F:1145-1153, 1188, 1203-1214); `step = ceil(fps/30)` sub-sampling (F:1127); skip when
+the .funscript exists unless `overwrite` (F:1105-1109).  The reference's prefetch race (SURVEY
+section 5.3) is *not* reproduced: every bracket is computed on its own frames.
+
+Frame acquisition (decode, resize to 256x256 or the VR crop, RGB->gray: F:1051-1091) stays on the
+host with cv2 -- it is outside the hot path; the hot path starts at the grayscale frames.
+"""
+from __future__ import annotations
+
+import math
+import os
+import time
+from typing import Callable, Dict, Iterable, List, Optional, Sequence
+
+import numpy as np
+
+from . import api, postproc
+
+SUPPORTED_VIDEO_EXTENSIONS = {".mp4", ".avi", ".mov", ".mkv", ".webm", ".flv", ".wmv", ".m4v", ".mpg", ".mpeg", ".ts"}
+
+
+def _brackets(n_frames: int, bracket: int):
+    for a in range(0, n_frames, bracket):
+        b = min(a + bracket, n_frames)
+        if b - a >= 2:      # F:1152-1153
+            yield a, b
+
+
+def process_frames(frames: Sequence[np.ndarray], fps: float, params: Dict, frame_indices: Optional[Sequence[int]] = None,
+                   ctx=None, progress_callback: Optional[Callable[[int], None]] = None,
+                   cancel_flag: Optional[Callable[[], bool]] = None, return_series: bool = False):
+    """Bracket loop (F:1145-1253) + post-processing (F:1266-1386) over in-memory sampled frames."""
+    n = len(frames)
+    idx = list(range(n)) if frame_indices is None else list(frame_indices)
+    bracket = int(params.get("batch_size", 3000.0))
+    values: List[float] = []
+    cuts: List[bool] = []
+    stamps: List[int] = []
+    for a, b in _brackets(n, bracket):
+        if cancel_flag and cancel_flag():
+            return None
+        r = api.process_bracket(frames[a:b], params, ctx=ctx, batch_frames=int(params.get("gpu_batch_frames", 16)))
+        values.extend(r["scalar"].tolist())
+        cuts.extend(r["cut"].tolist())
+        stamps.extend(idx[a:b - 1])          # F:1151: frame index of the first frame of each pair
+        if progress_callback:
+            progress_callback(min(100, int(100 * b / n)))
+    actions = postproc.scalars_to_actions(values, cuts, stamps, fps, params) if values else []
+    if return_series:
+        return actions, dict(values=np.asarray(values), cuts=np.asarray(cuts, bool), frame_indices=np.asarray(stamps))
+    return actions
+
+
+def read_sampled_gray(video_path: str, indices: Sequence[int], params: Dict) -> List[np.ndarray]:
+    """Frames `indices` of the video as the reference feeds them to the flow (F:1051-1091):
+    BGR->RGB, resize to 256x256 (VR: 512x512 then the bottom-left 256x256), RGB->gray."""
+    import cv2
+    cap = cv2.VideoCapture(video_path)
+    if not cap.isOpened():
+        raise IOError(f"cannot open {video_path}")
+    want = set(int(i) for i in indices)
+    last = max(want) if want else -1
+    out = []
+    pos = 0
+    vr = bool(params.get("vr_mode"))
+    while pos <= last:
+        if pos in want:
+            ok, frame = cap.read()
+            if not ok:      # F:274-280: undecodable frames become black
+                frame = np.zeros((256, 256, 3), np.uint8)
+            rgb = cv2.cvtColor(frame, cv2.COLOR_BGR2RGB)
+            if vr:
+                rgb = cv2.resize(rgb, (512, 512))[256:, :256]
+            else:
+                rgb = cv2.resize(rgb, (256, 256))
+            out.append(cv2.cvtColor(rgb, cv2.COLOR_RGB2GRAY))
+        else:
+            cap.grab()
+        pos += 1
+    cap.release()
+    return out
+
+
+def process_video(video_path, params, log_func, progress_callback=None, cancel_flag=None, preview_callback=None):
+    """Same contract as F:1094: writes <video>.funscript, returns error_occurred."""
+    import cv2
+    start = time.time()
+    base, _ = os.path.splitext(video_path)
+    output_path = base + ".funscript"
+    if os.path.exists(output_path) and not params["overwrite"]:
+        log_func(f"Skipping: output file exists ({output_path})")
+        return False
+    log_func(f"Processing video: {video_path}")
+    cap = cv2.VideoCapture(video_path)
+    if not cap.isOpened():
+        log_func(f"ERROR: Unable to open video at {video_path}")
+        return True
+    total = int(cap.get(cv2.CAP_PROP_FRAME_COUNT))
+    fps = float(cap.get(cv2.CAP_PROP_FPS))
+    cap.release()
+    if total < 2 or fps <= 0:
+        log_func("ERROR: Unable to read video properties")
+        return True
+    step = postproc.sampling_step(fps)
+    indices = list(range(0, total, step))
+    log_func(f"FPS: {fps:.2f}; downsampled to ~{fps / step:.2f} fps; {len(indices)} frames selected.")
+    log_func("Using backend: B200 (sm_100a)")
+    try:
+        frames = read_sampled_gray(video_path, indices, params)
+        actions = process_frames(frames, fps, params, indices[:len(frames)], progress_callback=progress_callback,
+                                 cancel_flag=cancel_flag)
+    except Exception as exc:   # surfaced, never swallowed into a CPU fallback
+        log_func(f"ERROR: {exc}")
+        return True
+    if actions is None:
+        log_func("User bailed.")
+        return False
+    log_func(f"Keyframe reduction: {len(actions)} actions computed.")
+    try:
+        postproc.write_funscript(output_path, actions)
+        log_func(f"Funscript saved: {output_path}")
+    except Exception as exc:
+        log_func(f"ERROR: {exc}")
+        return True
+    log_func(f"Processing time: {time.time() - start:.2f} seconds")
+    return False
+
+
+def list_videos(input_path: str) -> List[str]:
+    if os.path.isfile(input_path):
+        return [input_path]
+    found = []
+    for root, _, files in os.walk(input_path):
+        for f in sorted(files):
+            if os.path.splitext(f)[1].lower() in SUPPORTED_VIDEO_EXTENSIONS:
+                found.append(os.path.join(root, f))
+    return found
+
+
+def shard(items: Sequence, rank: int, world: int) -> List:
+    """Whole-video sharding across GPUs: video i goes to rank i % world."""
+    return [it for i, it in enumerate(items) if i % world == rank]
+
+
+def run_headless(input_path: str, settings: Dict, log_func: Callable[[str], None] = print) -> int:
+    """F:2606-2638.  Under torchrun (one process per GPU) each rank takes every world-th video."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    vids = shard(list_videos(input_path), rank, world)
+    errors = 0
+    for v in vids:
+        errors += bool(process_video(v, settings, log_func))
+    return errors

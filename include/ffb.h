@@ -140,6 +140,11 @@ int  ffb_profile(ffb_ctx* ctx, int enable);
 int  ffb_profile_reset(ffb_ctx* ctx);
 int  ffb_kernel_stats(ffb_ctx* ctx, int kernel_id, int64_t* launches, double* ms, double* alg_bytes);
 int64_t ffb_launch_count(const ffb_ctx* ctx);   /* kernels launched by this context so far */
+/* Device-side stopwatch on the compute stream (the stream every kernel is launched on):
+ * ffb_timer_mark(ctx, slot) records CUDA event `slot` (0..7); ffb_timer_elapsed waits for both
+ * events and returns the milliseconds between them. */
+int  ffb_timer_mark(ffb_ctx* ctx, int slot);
+int  ffb_timer_elapsed(ffb_ctx* ctx, int slot_from, int slot_to, double* ms);
 const char* ffb_kernel_name(int kernel_id);
 
 #ifdef __cplusplus

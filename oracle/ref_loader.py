@@ -60,7 +60,10 @@ def load(module_name: str = "ffref", serial_pools: bool = False) -> types.Module
     exec(_PRELUDE, mod.__dict__)
     if serial_pools:
         mod.Pool = _SerialPool
-        mod.concurrent = types.SimpleNamespace(futures=types.SimpleNamespace(ProcessPoolExecutor=_SerialExecutor))
+        import concurrent.futures as _cf
+        mod.concurrent = types.SimpleNamespace(futures=types.SimpleNamespace(
+            ProcessPoolExecutor=_SerialExecutor, ThreadPoolExecutor=_cf.ThreadPoolExecutor,
+            as_completed=_cf.as_completed))
     exec(compile(ast.Module(body=body, type_ignores=[]), REFERENCE_PYW, "exec"), mod.__dict__)
     sys.modules[module_name] = mod   # lets multiprocessing pickle the functions by name
     return mod

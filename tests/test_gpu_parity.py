@@ -1,0 +1,139 @@
+"""`-m gpu`: the parity tests proper.  The sm_100a library is called through the C ABI and compared
+with the oracle (oracle/), with cv2 (the dependency the reference calls at F:878) and with golden
+vectors recorded from the reference's own functions (tests/golden/).  Nothing here reads
+/root/reference."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import parity_checks as pc
+from funscript_flow_b200 import api, postproc, runner
+from funscript_flow_b200.synth import ClipGenerator, ClipSpec, make_clip
+from oracle import motion_np as mo
+
+pytestmark = pytest.mark.gpu
+cv2 = pytest.importorskip("cv2")
+
+
+@pytest.mark.parametrize("size", [(150, 101), (517, 389), (640, 360)])
+def test_stages(gpu_ctx, size):
+    pc.check_stages(gpu_ctx, *size)
+
+
+@pytest.mark.parametrize("size", [(256, 256), (640, 360), (333, 217), (517, 389), (1920, 1080)])
+def test_farneback_vs_cv2(gpu_ctx, size):
+    print(pc.check_farneback_vs_cv2(gpu_ctx, *size))
+
+
+@pytest.mark.parametrize("size", [(3840, 2160), (5760, 2880)])
+def test_farneback_vs_cv2_large(gpu_ctx, size):
+    """Configs C3 / C4 frame sizes (largest per-frame working set)."""
+    print(pc.check_farneback_vs_cv2(gpu_ctx, *size, period=20.0, amplitude=0.1))
+
+
+def test_reduction_known_answers(gpu_ctx, golden_dir):
+    pc.check_reductions_kat(gpu_ctx, golden_dir)
+
+
+def test_golden_pairs(gpu_ctx, golden_dir):
+    pc.check_golden_pairs(gpu_ctx, golden_dir)
+
+
+def test_golden_bracket(gpu_ctx, golden_dir):
+    pc.check_golden_bracket(gpu_ctx, golden_dir)
+    pc.check_golden_bracket(gpu_ctx, golden_dir, batch_frames=64)
+
+
+def test_edge_brackets(gpu_ctx):
+    pc.check_edge_brackets(gpu_ctx)
+
+
+def test_batch_independence_1080p(gpu_ctx):
+    """Full-size property (BASELINE config C2 frame size): results are bit-identical however the
+    frames are batched / pushed, which is also what makes bracket sharding across GPUs exact."""
+    pc.check_batch_independence(gpu_ctx, 1920, 1080, n_frames=20)
+
+
+def test_bracket_vs_oracle_640x360(gpu_ctx):
+    """Config C1 geometry: per-pair centres (margin-guarded), cut flags and scalars vs the oracle."""
+    clip = ClipGenerator(ClipSpec(640, 360, 24, seed=0, amplitude=0.15, period=30.0)).stack(3, 27)
+    vals, cuts, infos = mo.process_bracket(list(clip), {})
+    r = api.process_bracket(clip, {}, ctx=gpu_ctx, batch_frames=8, return_flows=True)
+    assert np.array_equal(r["cut"], cuts)
+    exact = 0
+    for j, info in enumerate(infos):
+        pc.assert_flow_close(r["flows"][j - r["flow_first"]], info["flow"], f"pair {j}") if j >= r["flow_first"] else None
+        exact += pc.assert_argmax((r["cx"][j], r["cy"][j]), r["val"][j], info["flow"], f"pair {j}") >= pc.ARGMAX_MARGIN
+        ref = mo.radial_motion_weighted(info["flow"], r["centers"][j], info["cut"])
+        assert abs(r["scalar"][j] - ref) <= pc.SCALAR_RTOL * abs(ref) + pc.scalar_tol(info["flow"], r["centers"][j])
+    assert exact >= len(infos) // 2
+    same = np.all(np.stack([r["cx"], r["cy"]], 1) == np.array([i["pos_center"] for i in infos]), axis=1)
+    if same.all():
+        assert np.allclose(r["scalar"], vals, rtol=pc.SCALAR_RTOL, atol=1e-6)
+
+
+def test_scene_cuts_and_pan(gpu_ctx):
+    """Config C3 style (pan + hard cuts) at a CPU-checkable size: identical scene-cut indices."""
+    spec = ClipSpec(960, 540, 40, seed=3, amplitude=0.15, period=20.0, pan=(1.5, 0.0), cuts=(13, 29))
+    clip = ClipGenerator(spec).stack()
+    thr = 3.0
+    ref_mm = np.array([mo.mean_magnitude(cv2.calcOpticalFlowFarneback(a, b, None, 0.5, 3, 15, 3, 5, 1.2, 0))
+                       for a, b in zip(clip[:-1], clip[1:])])
+    r = api.process_bracket(clip, {"cut_threshold": thr}, ctx=gpu_ctx, batch_frames=16)
+    assert np.allclose(r["mean_mag"], ref_mm, rtol=pc.MEAN_MAG_RTOL, atol=1e-6)
+    clear = np.abs(ref_mm - thr) > 0.05          # margin guard
+    assert clear[[12, 28]].all() and (ref_mm[[12, 28]] > thr).all(), "clip no longer has clear cuts"
+    assert np.array_equal(r["cut"][clear], (ref_mm > thr)[clear])
+    assert np.flatnonzero(r["cut"]).tolist() == np.flatnonzero(ref_mm > thr).tolist()
+    assert (r["scalar"][r["cut"]] == 0.0).all()
+
+
+def test_dropin_functions(gpu_ctx):
+    """Module-level functions with the reference's signatures (F:748, F:761, F:843, F:982, F:1019)."""
+    api.set_context(gpu_ctx)
+    clip = make_clip(320, 240, 4, seed=12, period=9.0, amplitude=0.3)
+    ref = mo.precompute_flow_info(clip[1], clip[2], {})
+    for info in (api.precompute_flow_info(clip[1], clip[2], {"backend": "CUDA"}),
+                 api.precompute_flow_info_gpu(clip[1], clip[2], 7),
+                 api.precompute_wrapper((clip[1], clip[2]), {"threads": 8})):
+        pc.assert_flow_close(info["flow"], ref["flow"], "drop-in")
+        assert info["flow"].dtype == np.float32 and info["flow"].shape == (240, 320, 2)
+        assert isinstance(info["cut"], bool) and info["cut"] == ref["cut"]
+        assert isinstance(info["mean_mag"], np.float32) and isinstance(info["val_pos"], np.float32)
+    x, y, v = api.max_divergence(ref["flow"])
+    assert (int(x), int(y)) == tuple(ref["pos_center"]) and v == ref["val_pos"]      # bit-exact on equal input
+    for c in ([100.5, 80.25], [160.0, 120.0]):
+        for pov in (False, True):
+            a = api.radial_motion_weighted(ref["flow"], c, False, pov)
+            b = mo.radial_motion_weighted(ref["flow"], c, False, pov)
+            assert abs(a - b) <= 1e-6 * abs(b) + pc.scalar_tol(ref["flow"], c)
+    assert api.radial_motion_weighted(ref["flow"], [1, 1], True) == 0.0
+    assert api.get_available_backends()["CUDA"] is True
+
+
+def test_process_video_matches_reference_funscript(gpu_ctx, golden_dir, tmp_path):
+    """End to end on the C1-style clip: the .funscript written by our process_video() has the same
+    keyframe timestamps as the one the reference's process_video() wrote (recorded in video_c1.json)."""
+    api.set_context(gpu_ctx)
+    g = json.load(open(os.path.join(golden_dir, "video_c1.json")))
+    s = g["spec"]
+    clip = ClipGenerator(ClipSpec(s["width"], s["height"], s["n_frames"], seed=s["seed"], amplitude=s["amplitude"],
+                                  period=s["period"])).stack()
+    path = str(tmp_path / "c1.avi")
+    vw = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"FFV1"), s["fps"], (s["width"], s["height"]), True)
+    if not vw.isOpened():
+        pytest.skip("FFV1 writer unavailable on this box")
+    for f in clip:
+        vw.write(cv2.cvtColor(f, cv2.COLOR_GRAY2BGR))
+    vw.release()
+    logs = []
+    assert runner.process_video(path, g["settings"], logs.append) is False, logs
+    acts = json.load(open(str(tmp_path / "c1.funscript")))["actions"]
+    assert [a["at"] for a in acts] == [a["at"] for a in g["actions"]], (acts, g["actions"])
+    assert max(abs(a["pos"] - b["pos"]) for a, b in zip(acts, g["actions"])) <= 1
+    # a second call skips because the output exists (F:1105-1109)
+    logs.clear()
+    assert runner.process_video(path, dict(g["settings"], overwrite=False), logs.append) is False
+    assert any("Skipping" in l for l in logs)

@@ -1,0 +1,63 @@
+"""CPU suite, part 4: the N>1 host logic with world_size 2 over gloo (no GPU): bracket sharding and
+the gather of per-pair scalars give exactly the single-process result.  The compute engine in this
+test is the g++ emulation of the kernels (test infrastructure)."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r"""
+import json, os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import numpy as np
+from funscript_flow_b200 import _native, api, distributed
+from funscript_flow_b200.synth import make_clip
+ctx = _native.FlowContext(0, {emu!r})
+api.set_context(ctx)
+rank, ws = distributed.init("gloo")
+clip = make_clip(96, 64, 17, seed=8, period=7.0, amplitude=0.3)
+prm = {{"batch_size": 6, "detrend_window": 2.0, "norm_window": 3.0, "keyframe_reduction": True}}
+acts, series = distributed.process_frames_sharded(clip, 30.0, prm, ctx=ctx)
+if rank == 0:
+    json.dump({{"actions": acts, "values": series["values"].tolist(), "idx": series["frame_indices"].tolist(),
+               "ws": ws}}, open({out!r}, "w"))
+import torch.distributed as dist
+if dist.is_initialized():
+    dist.barrier(); dist.destroy_process_group()
+"""
+
+
+def run(nproc, emu_lib, out, port):
+    script = WORKER.format(root=ROOT, emu=emu_lib, out=out)
+    path = out + ".py"
+    open(path, "w").write(script)
+    if nproc == 1:
+        env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+        subprocess.run([sys.executable, path], check=True, env=env, timeout=600)
+    else:
+        subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), path], check=True, timeout=900)
+    return json.load(open(out))
+
+
+def test_bracket_sharding_world2_equals_single(emu_lib, tmp_path):
+    single = run(1, emu_lib, str(tmp_path / "single.json"), 0)
+    multi = run(2, emu_lib, str(tmp_path / "multi.json"), 29517)
+    assert multi["ws"] == 2 and single["ws"] == 1
+    assert single["idx"] == [0, 1, 2, 3, 4, 6, 7, 8, 9, 10, 12, 13, 14, 15]   # 3 brackets of 6,6,5 frames
+    assert multi["idx"] == single["idx"]
+    assert multi["values"] == single["values"]          # bit-for-bit
+    assert multi["actions"] == single["actions"]
+
+
+def test_video_sharding():
+    from funscript_flow_b200 import distributed, runner
+    vids = [f"v{i}" for i in range(10)]
+    parts = [runner.shard(vids, r, 4) for r in range(4)]
+    assert sorted(sum(parts, [])) == sorted(vids) and max(map(len, parts)) - min(map(len, parts)) <= 1
+    assert distributed.bracket_ranges(11, 5) == [(0, 5), (5, 10)]
+    assert distributed.my_brackets([(0, 5), (5, 10), (10, 15)], 1, 2) == [1]
