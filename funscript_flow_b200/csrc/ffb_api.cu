@@ -364,38 +364,68 @@ int launch_upsample(ffb_ctx* c, const float2* src, size_t src_stride, int sp, in
     return FFB_OK;
 }
 
-constexpr int IT_NT = 128, IT_U = 4;
+// Tunables of the fused iteration kernel (threads per CTA x rows per step, rows per segment).
+// Defaults are compiled in; FFB_ITER_CFG=NTxU and FFB_ITER_SH=rows override them for tuning runs.
+struct IterCfg { int nt, u, sh; };
+IterCfg iter_cfg() {
+    static IterCfg cfg = [] {
+        IterCfg c{128, 2, 120};
+        if (const char* e = getenv("FFB_ITER_CFG")) {
+            int nt = 0, u = 0;
+            if (sscanf(e, "%dx%d", &nt, &u) == 2) { c.nt = nt; c.u = u; }
+        }
+        if (const char* e = getenv("FFB_ITER_SH")) { const int v = atoi(e); if (v >= 16) c.sh = v; }
+        return c;
+    }();
+    return cfg;
+}
 
-int launch_flow_iter(ffb_ctx* c, FfbRing R, size_t plane, int rp, int w, int h, const float2* fin, size_t fin_stride,
-                     int fip, FfbRing fout, int fop, int npairs) {
-    FfbIterArgs a;
-    a.R = R; a.plane = plane; a.rp = rp; a.w = w; a.h = h;
-    a.fin = fin; a.fin_stride = fin_stride; a.fip = fip; a.fout = fout; a.fop = fop;
-    const int sw_max = (IT_NT - 2 * FFB_WIN_R) / 4 * 4;
+template <int NT, int U>
+int launch_flow_iter_t(ffb_ctx* c, FfbIterArgs a, int npairs, int sh_target, double bytes) {
+    const int w = a.w, h = a.h;
+    const int sw_max = (NT - 2 * FFB_WIN_R) / 4 * 4;
     const int nstrips = (w + sw_max - 1) / sw_max;
     a.SW = ffb_round_up((w + nstrips - 1) / nstrips, 4);
     if (a.SW > sw_max) a.SW = sw_max;
     const int gx = (w + a.SW - 1) / a.SW;
-    // enough CTAs for ~2 waves of 148 SMs x 3 resident CTAs, but segments of at least 48 rows
-    const int target = 148 * 3 * 2;
-    int nseg = (target + gx * npairs - 1) / (gx * npairs);
-    const int max_seg = h / 48 > 1 ? h / 48 : 1;
-    if (nseg > max_seg) nseg = max_seg;
+    // Row segments depend on the level geometry only (never on the batch composition), so a pair's
+    // result is bit-identical however frames are batched or sharded.
+    int nseg = (h + sh_target / 2) / sh_target;
     if (nseg < 1) nseg = 1;
     a.SH = (h + nseg - 1) / nseg;
     const int gy = (h + a.SH - 1) / a.SH;
-    auto kfn = k_flow_iter<IT_NT, IT_U>;
-    const size_t smem = ffb_flow_iter_smem<IT_NT, IT_U>();
+    auto kfn = k_flow_iter<NT, U>;
+    const size_t smem = ffb_flow_iter_smem<NT, U>();
     static bool attr_set = false;
     if (!attr_set) {
         CK(c, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    prof_begin(c, FFB_K_FLOW_ITER, (double)npairs * (fin ? 56.0 : 48.0) * w * h);
-    FFB_LAUNCH(kfn, dim3(gx, gy, npairs), dim3(IT_NT), smem, c->s_comp, a);
+    prof_begin(c, FFB_K_FLOW_ITER, bytes);
+    FFB_LAUNCH(kfn, dim3(gx, gy, npairs), dim3(NT), smem, c->s_comp, a);
     prof_end(c);
     CKL(c);
     return FFB_OK;
+}
+
+int launch_flow_iter(ffb_ctx* c, FfbRing R, size_t plane, int rp, int w, int h, const float2* fin, size_t fin_stride,
+                     int fip, FfbRing fout, int fop, int npairs) {
+    FfbIterArgs a;
+    a.R = R; a.plane = (int)plane; a.rp = rp; a.w = w; a.h = h;
+    a.fin = fin; a.fin_stride = fin_stride; a.fip = fip; a.fout = fout; a.fop = fop;
+    a.SW = a.SH = 0;
+    const double bytes = (double)npairs * (fin ? 56.0 : 48.0) * w * h;
+    const IterCfg k = iter_cfg();
+    const int key = k.nt * 10 + k.u;
+    switch (key) {
+        case 1282: return launch_flow_iter_t<128, 2>(c, a, npairs, k.sh, bytes);
+        case 1922: return launch_flow_iter_t<192, 2>(c, a, npairs, k.sh, bytes);
+        case 1924: return launch_flow_iter_t<192, 4>(c, a, npairs, k.sh, bytes);
+        case 2562: return launch_flow_iter_t<256, 2>(c, a, npairs, k.sh, bytes);
+        case 2564: return launch_flow_iter_t<256, 4>(c, a, npairs, k.sh, bytes);
+        case 1281: return launch_flow_iter_t<128, 1>(c, a, npairs, k.sh, bytes);
+        default:   return launch_flow_iter_t<128, 4>(c, a, npairs, k.sh, bytes);
+    }
 }
 
 // ------------------------------------------------------------------ geometry

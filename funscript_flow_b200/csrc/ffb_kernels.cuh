@@ -294,16 +294,20 @@ __global__ void __launch_bounds__(256) k_update_matrices(FfbMatArgs a) {
 // K3  fused flow iteration: matrices -> 15x15 box mean (replicate border) -> 2x2 solve
 // ======================================================================================
 // One CTA owns a strip of SW output columns (plus a 7-column halo on each side: one thread per
-// M column) and marches down a segment of SH rows.  The matrices never touch HBM:
-//   * each thread computes the 5-vector M of its column for U new rows (the R1 gather),
-//   * keeps a Kahan-compensated running sum over the last 15 rows (the column ring of raw M
-//     values lives in shared memory so the row leaving the window can be subtracted),
-//   * publishes its vertical sums to a shared row buffer,
-//   * and a quarter of the threads then form the horizontal 15-sums for 4 adjacent outputs from
-//     five aligned 16-byte shared loads per channel, solve the 2x2 system and store float2 x 4.
+// M column) and marches down a segment of SH rows, U rows per step.  The matrices never touch HBM:
+//   * each thread gathers the inputs of the 5-vector M of its column for U new rows.  All loads are
+//     unconditional (the R1 footprint is clamped into the image and the out-of-bounds fallback is
+//     selected afterwards), so the 25*U loads of a step are issued back to back, and they are
+//     issued BEFORE the horizontal phase of the previous step so their latency overlaps it; the
+//     flow of the next step is prefetched one step ahead (it feeds the gather addresses),
+//   * a Kahan-compensated running sum over the last 15 rows is kept per column (the column ring of
+//     raw M values lives in shared memory so the row leaving the window can be subtracted),
+//   * the vertical sums are published to a double-buffered shared row buffer,
+//   * a quarter of the threads form the horizontal 15-sums for 4 adjacent outputs from five aligned
+//     16-byte shared loads per channel, solve the 2x2 system and store float2 x 4.
 struct FfbIterArgs {
     FfbRing R;              // frame expansions: pair j uses elements j (prev) and j+1 (next)
-    size_t plane; int rp; int w, h;
+    int plane; int rp; int w, h;                     // plane = rp * h floats (< 2^31 / 5)
     const float2* fin; size_t fin_stride; int fip;   // flow in (NULL = zero), strides in float2
     FfbRing fout; int fop;                           // flow out ring (element j), pitch in float2
     int SW;                 // output columns per strip (multiple of 4, <= NT - 14)
@@ -312,6 +316,72 @@ struct FfbIterArgs {
 
 template <int NT, int U>
 __host__ __device__ constexpr size_t ffb_flow_iter_smem() { return sizeof(float) * (2 * U * 5 * (NT + 4) + FFB_WIN * 5 * NT); }
+
+// Raw inputs of one matrix update, as loaded (all loads unconditional).
+struct FfbGather {
+    float r0[5];      // R0 at the pixel
+    float t[5][4];    // R1 footprint per channel: (y1,x1) (y1,x1+1) (y1+1,x1) (y1+1,x1+1), clamped into the image
+    float fx, fy;     // fractional parts
+    float dx, dy;
+    int inside;
+};
+
+__device__ __forceinline__ void ffb_gather_issue(const float* __restrict__ R0, const float* __restrict__ R1, int plane,
+                                                 int rp, int w, int h, int x, int y, float2 d, FfbGather& g) {
+    float fx = (float)x + d.x, fy = (float)y + d.y;
+    const float x1f = floorf(fx), y1f = floorf(fy);
+    const int x1 = (int)x1f, y1 = (int)y1f;
+    g.fx = fx - x1f;
+    g.fy = fy - y1f;
+    g.dx = d.x;
+    g.dy = d.y;
+    g.inside = ((unsigned)x1 < (unsigned)(w - 1)) && ((unsigned)y1 < (unsigned)(h - 1));
+    const int xs = min(max(x1, 0), w - 2), ys = min(max(y1, 0), h - 2);
+    const float* q = R0 + (y * rp + x);
+    const float* p = R1 + (ys * rp + xs);
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        g.r0[c] = __ldg(q + c * plane);
+        g.t[c][0] = __ldg(p + c * plane);
+        g.t[c][1] = __ldg(p + c * plane + 1);
+        g.t[c][2] = __ldg(p + c * plane + rp);
+        g.t[c][3] = __ldg(p + c * plane + rp + 1);
+    }
+}
+
+__device__ __forceinline__ void ffb_gather_finish(const FfbGather& g, int w, int h, int x, int y, float m[5]) {
+    const float fx = g.fx, fy = g.fy;
+    const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
+    float s[5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) s[c] = a00 * g.t[c][0] + a01 * g.t[c][1] + a10 * g.t[c][2] + a11 * g.t[c][3];
+    float r2, r3, r4, r5, r6;
+    if (g.inside) {
+        r2 = s[0];
+        r3 = s[1];
+        r4 = (g.r0[2] + s[2]) * 0.5f;
+        r5 = (g.r0[3] + s[3]) * 0.5f;
+        r6 = (g.r0[4] + s[4]) * 0.25f;
+    } else {
+        r2 = r3 = 0.f;
+        r4 = g.r0[2];
+        r5 = g.r0[3];
+        r6 = g.r0[4] * 0.5f;
+    }
+    r2 = (g.r0[0] - r2) * 0.5f;
+    r3 = (g.r0[1] - r3) * 0.5f;
+    r2 += r4 * g.dy + r6 * g.dx;
+    r3 += r6 * g.dy + r5 * g.dx;
+    if ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10)) {
+        const float sc = ffb_border_w(x) * ffb_border_w(w - x - 1) * ffb_border_w(y) * ffb_border_w(h - y - 1);
+        r2 *= sc; r3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
+    }
+    m[0] = r4 * r4 + r6 * r6;
+    m[1] = (r4 + r5) * r6;
+    m[2] = r5 * r5 + r6 * r6;
+    m[3] = r4 * r2 + r6 * r3;
+    m[4] = r6 * r2 + r5 * r3;
+}
 
 template <int NT, int U>
 __global__ void __launch_bounds__(NT) k_flow_iter(FfbIterArgs a) {
@@ -336,6 +406,11 @@ __global__ void __launch_bounds__(NT) k_flow_iter(FfbIterArgs a) {
     const int nfeed = (y1 - y0) + 2 * FFB_WIN_R;
     const int nsteps = (nfeed + U - 1) / U;
     const int groups = a.SW >> 2;
+    // horizontal-phase role of this thread (fixed for the whole kernel)
+    const bool hz = tid < U * groups;
+    const int hu = hz ? tid / groups : 0;
+    const int hg = hz ? tid - hu * groups : 0;
+    const int hx = xo0 + 4 * hg;
 
 #pragma unroll
     for (int s = 0; s < FFB_WIN; ++s)
@@ -352,33 +427,84 @@ __global__ void __launch_bounds__(NT) k_flow_iter(FfbIterArgs a) {
     float vs[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, comp[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     int slot = 0;
 
+    // horizontal sums + solve + store of the U rows published by step `s` into buffer `buf`
+    auto horizontal = [&](int s, int buf) {
+        const int i = s * U + hu;
+        if (!hz || i < 2 * FFB_WIN_R || i >= nfeed || hx >= w) return;
+        const int yo = y0 + i - 2 * FFB_WIN_R;
+        float sum[5][4];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            const float4* hp = reinterpret_cast<const float4*>(&hrow[buf][hu][c][4 * hg]);
+            const float4 q0 = hp[0], q1 = hp[1], q2 = hp[2], q3 = hp[3], q4 = hp[4];
+            // window of output 0 = elements 0..14; each next output drops one, adds one
+            const float mid = ((q0.w + q1.x) + (q1.y + q1.z)) + ((q1.w + q2.x) + (q2.y + q2.z)) +
+                              ((q2.w + q3.x) + (q3.y + q3.z));          // elements 3..14
+            sum[c][0] = mid + ((q0.x + q0.y) + q0.z);
+            sum[c][1] = mid + ((q0.y + q0.z) + q3.w);
+            sum[c][2] = mid + ((q0.z + q3.w) + q4.x);
+            sum[c][3] = mid + ((q3.w + q4.x) + q4.y);
+        }
+        float2 o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float sc = 1.f / (float)(FFB_WIN * FFB_WIN);
+            const float g11 = sum[0][j] * sc, g12 = sum[1][j] * sc, g22 = sum[2][j] * sc;
+            const float h1 = sum[3][j] * sc, h2 = sum[4][j] * sc;
+            // det = g11*g22 - g12*g12 with an exact-product correction (Kahan's ad-bc)
+            const float wq = g12 * g12;
+            const float e = __fmaf_rn(-g12, g12, wq);
+            const float fd = __fmaf_rn(g11, g22, -wq);
+            const float idet = 1.f / ((fd + e) + 1e-3f);
+            o[j].x = (g11 * h2 - g12 * h1) * idet;
+            o[j].y = (g22 * h1 - g12 * h2) * idet;
+        }
+        float2* dst = fout + (yo * a.fop + hx);
+        if (hx + 3 < w) {
+            reinterpret_cast<float4*>(dst)[0] = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
+            reinterpret_cast<float4*>(dst)[1] = make_float4(o[2].x, o[2].y, o[3].x, o[3].y);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (hx + j < w) dst[j] = o[j];
+        }
+    };
+
+    auto load_flow = [&](int s, float2 (&d)[U]) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int yc = ffb_clampi(y0 - FFB_WIN_R + s * U + u, 0, h - 1);
+            d[u] = fin ? __ldg(fin + (yc * a.fip + xc)) : make_float2(0.f, 0.f);
+        }
+    };
+
+    float2 d[U], dn[U];
+    load_flow(0, d);
     for (int s = 0; s < nsteps; ++s) {
         const int buf = s & 1;
-        // ---- gather phase: U rows of matrices for this thread's column
-        float m[U][5];
+        // ---- issue the gather of step s (25*U independent loads), then the flow prefetch of step s+1
+        FfbGather g[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int yc = ffb_clampi(y0 - FFB_WIN_R + s * U + u, 0, h - 1);
+            ffb_gather_issue(R0, R1, a.plane, a.rp, w, h, xc, yc, d[u], g[u]);
+        }
+        load_flow(s + 1, dn);
+        // ---- while those are in flight: horizontal phase of the previous step
+        if (s > 0) horizontal(s - 1, buf ^ 1);
+        // ---- matrices + vertical running sums (Kahan-compensated add of  new - leaving)
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int i = s * U + u;
             if (i < nfeed) {
                 const int yc = ffb_clampi(y0 - FFB_WIN_R + i, 0, h - 1);
-                float2 d = make_float2(0.f, 0.f);
-                if (fin) d = __ldg(fin + (size_t)yc * a.fip + xc);
-                ffb_compute_M(R0, R1, a.plane, a.rp, w, h, xc, yc, d.x, d.y, m[u]);
-            } else {
-#pragma unroll
-                for (int c = 0; c < 5; ++c) m[u][c] = 0.f;
-            }
-        }
-        // ---- vertical running sums (Kahan-compensated add of  new - leaving)
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int i = s * U + u;
-            if (i < nfeed) {
+                float m[5];
+                ffb_gather_finish(g[u], w, h, xc, yc, m);
 #pragma unroll
                 for (int c = 0; c < 5; ++c) {
                     const float old = ring[slot][c][tid];
-                    ring[slot][c][tid] = m[u][c];
-                    const float yk = (m[u][c] - old) - comp[c];
+                    ring[slot][c][tid] = m[c];
+                    const float yk = (m[c] - old) - comp[c];
                     const float t = vs[c] + yk;
                     comp[c] = (t - vs[c]) - yk;
                     vs[c] = t;
@@ -389,54 +515,10 @@ __global__ void __launch_bounds__(NT) k_flow_iter(FfbIterArgs a) {
             for (int c = 0; c < 5; ++c) hrow[buf][u][c][tid] = vs[c];
         }
         __syncthreads();
-        // ---- horizontal sums + solve for 4 adjacent outputs
-        if (tid < U * groups) {
-            const int u = tid / groups, g = tid - u * groups;
-            const int i = s * U + u;
-            const int x = xo0 + 4 * g;
-            if (i >= 2 * FFB_WIN_R && i < nfeed && x < w) {
-                const int yo = y0 + i - 2 * FFB_WIN_R;
-                float sum[5][4];
 #pragma unroll
-                for (int c = 0; c < 5; ++c) {
-                    const float4* hp = reinterpret_cast<const float4*>(&hrow[buf][u][c][4 * g]);
-                    const float4 q0 = hp[0], q1 = hp[1], q2 = hp[2], q3 = hp[3], q4 = hp[4];
-                    // window of output 0 = elements 0..14; each next output drops one, adds one
-                    const float mid = ((q0.w + q1.x) + (q1.y + q1.z)) + ((q1.w + q2.x) + (q2.y + q2.z)) +
-                                      ((q2.w + q3.x) + (q3.y + q3.z));          // elements 3..14
-                    sum[c][0] = mid + ((q0.x + q0.y) + q0.z);
-                    sum[c][1] = mid + ((q0.y + q0.z) + q3.w);
-                    sum[c][2] = mid + ((q0.z + q3.w) + q4.x);
-                    sum[c][3] = mid + ((q3.w + q4.x) + q4.y);
-                }
-                float2 o[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float sc = 1.f / (float)(FFB_WIN * FFB_WIN);
-                    const float g11 = sum[0][j] * sc, g12 = sum[1][j] * sc, g22 = sum[2][j] * sc;
-                    const float h1 = sum[3][j] * sc, h2 = sum[4][j] * sc;
-                    // det = g11*g22 - g12*g12 with an exact-product correction (Kahan's ad-bc)
-                    const float wq = g12 * g12;
-                    const float e = __fmaf_rn(-g12, g12, wq);
-                    const float fd = __fmaf_rn(g11, g22, -wq);
-                    const float idet = 1.f / ((fd + e) + 1e-3f);
-                    o[j].x = (g11 * h2 - g12 * h1) * idet;
-                    o[j].y = (g22 * h1 - g12 * h2) * idet;
-                }
-                float2* dst = fout + (size_t)yo * a.fop + x;
-                if (x + 3 < w) {
-                    reinterpret_cast<float4*>(dst)[0] = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
-                    reinterpret_cast<float4*>(dst)[1] = make_float4(o[2].x, o[2].y, o[3].x, o[3].y);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (x + j < w) dst[j] = o[j];
-                }
-            }
-        }
-        // hrow is double-buffered: the barrier of the next step orders these reads before the
-        // writes of step s+2 into the same buffer.
+        for (int u = 0; u < U; ++u) d[u] = dn[u];
     }
+    horizontal(nsteps - 1, (nsteps - 1) & 1);
 }
 
 // ======================================================================================

@@ -67,7 +67,9 @@ def scalar_tol(flow, center):
     h, w = flow.shape[:2]
     xs = np.arange(w)[None, :] - center[0]
     ys = np.arange(h)[:, None] - center[1]
-    return 1e-6 * float(np.mean(np.abs(flow[..., 0] * xs) + np.abs(flow[..., 1] * ys)))
+    # floor = 1e-4 x mean |term|: the flow itself only agrees with cv2 to ~1e-5 px at p99 (plus a few
+    # border pixels at ~0.1 px), and near-stationary pairs have scalars 1000x smaller than their terms
+    return 1e-4 * float(np.mean(np.abs(flow[..., 0] * xs) + np.abs(flow[..., 1] * ys)))
 
 
 # ---- stage-wise checks -----------------------------------------------------------------------
