@@ -186,6 +186,7 @@ struct ffb_ctx {
     FfbPolyConsts poly;
     // geometry
     int W = 0, H = 0, B = 0, maxPairs = 0, nlev = 0, S = 0, ring_n = 0, fp0 = 0;
+    bool pyr_fast = false;
     Level lev[FFB_MAX_LEVELS];
     float* R = nullptr;
     size_t r_slot_floats = 0;
@@ -322,11 +323,16 @@ int launch_pyramid(ffb_ctx* c, const uint8_t* src, size_t src_stride, int src_pi
     a.src = src; a.src_frame_stride = src_stride; a.src_pitch = src_pitch; a.W = W; a.H = H;
     a.dst = dst; a.dst_frame_stride = dst_stride; a.dp = dp; a.w = w; a.h = h;
     a.xi = xi; a.xa = xa; a.yi = yi; a.ya = ya; a.taps = taps;
-    a.RWp = ffb_round_up(RW, 4);
-    a.p_off = ffb_round_up(a.RWp * RH, 16);
-    const size_t smem = (size_t)a.p_off + (size_t)RH * PYR_TW * sizeof(float);
+    a.RWp = RW | 1;                       // odd pitch: column walks of pass 1 stay conflict-free
+    a.p_off = ffb_round_up(a.RWp * RH, 4);
+    const size_t smem = ((size_t)a.p_off + (size_t)RH * PYR_TW) * sizeof(float);
+    if (taps.r >= W || taps.r >= H) return fail(c, FFB_E_INVALID, "frame smaller than the blur radius");
     auto kfn = k_pyramid_level<PYR_TW, PYR_TH>;
-    if (smem > 48 * 1024) CK(c, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static size_t smem_max = 48 * 1024;
+    if (smem > smem_max) {
+        CK(c, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_max = smem;
+    }
     dim3 grid((w + PYR_TW - 1) / PYR_TW, (h + PYR_TH - 1) / PYR_TH, nframes);
     prof_begin(c, FFB_K_PYRAMID, (double)nframes * ((double)W * H + 4.0 * w * h));
     FFB_LAUNCH(kfn, grid, dim3(PYR_TW * PYR_TH), smem, c->s_comp, a);
@@ -340,10 +346,14 @@ int launch_polyexp(ffb_ctx* c, const float* src, size_t src_stride, int sp, int 
     FfbPolyArgs a;
     a.src = src; a.src_frame_stride = src_stride; a.sp = sp; a.w = w; a.h = h;
     a.dst = dst; a.plane = plane; a.rp = rp; a.c = c->poly;
-    auto kfn = k_polyexp<32, 8>;
-    dim3 grid((w + 31) / 32, (h + 7) / 8, nframes);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CK(c, cudaFuncSetAttribute(k_polyexp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POLY_SMEM));
+        attr_set = true;
+    }
+    dim3 grid((w + POLY_OW - 1) / POLY_OW, (h + POLY_ROWS - 1) / POLY_ROWS, nframes);
     prof_begin(c, FFB_K_POLYEXP, (double)nframes * 24.0 * w * h);
-    FFB_LAUNCH(kfn, grid, dim3(256), 0, c->s_comp, a);
+    FFB_LAUNCH(k_polyexp, grid, dim3(256), POLY_SMEM, c->s_comp, a);
     prof_end(c);
     CKL(c);
     return FFB_OK;
@@ -402,19 +412,36 @@ int launch_flow_iter_t(ffb_ctx* c, FfbIterArgs a, int npairs, int sh_target, dou
         attr_set = true;
     }
     prof_begin(c, FFB_K_FLOW_ITER, bytes);
-    FFB_LAUNCH(kfn, dim3(gx, gy, npairs), dim3(NT), smem, c->s_comp, a);
+    // pair index varies fastest in launch order: the CTAs working on one spatial tile of consecutive
+    // pairs are co-resident, so frame j+1's expansion (R1 of pair j, R0 of pair j+1) is read from
+    // HBM once and hit in L2 the second time.
+    FFB_LAUNCH(kfn, dim3(npairs, gx, gy), dim3(NT), smem, c->s_comp, a);
     prof_end(c);
     CKL(c);
     return FFB_OK;
 }
 
+struct UpSrc {   // coarser-level flow to be up-sampled inside the iteration kernel (A1e fused)
+    const float2* src = nullptr; size_t stride = 0; int sp = 0, wc = 0, hc = 0;
+    const int *xi = nullptr, *yi = nullptr; const float *xa = nullptr, *ya = nullptr;
+};
+
 int launch_flow_iter(ffb_ctx* c, FfbRing R, size_t plane, int rp, int w, int h, const float2* fin, size_t fin_stride,
-                     int fip, FfbRing fout, int fop, int npairs) {
+                     int fip, FfbRing fout, int fop, int npairs, const UpSrc* up = nullptr) {
     FfbIterArgs a;
     a.R = R; a.plane = (int)plane; a.rp = rp; a.w = w; a.h = h;
     a.fin = fin; a.fin_stride = fin_stride; a.fip = fip; a.fout = fout; a.fop = fop;
     a.SW = a.SH = 0;
-    const double bytes = (double)npairs * (fin ? 56.0 : 48.0) * w * h;
+    a.up_src = nullptr; a.up_stride = 0; a.usp = a.wc = a.hc = 0;
+    a.uxi = a.uyi = nullptr; a.uxa = a.uya = nullptr;
+    double bpp = fin ? 56.0 : 48.0;
+    if (up && up->src) {
+        a.up_src = up->src; a.up_stride = up->stride; a.usp = up->sp; a.wc = up->wc; a.hc = up->hc;
+        a.uxi = up->xi; a.uxa = up->xa; a.uyi = up->yi; a.uya = up->ya;
+        a.fin = nullptr;
+        bpp = 48.0 + 8.0 * ((double)up->wc * up->hc) / ((double)w * h);
+    }
+    const double bytes = (double)npairs * bpp * w * h;
     const IterCfg k = iter_cfg();
     const int key = k.nt * 10 + k.u;
     switch (key) {
@@ -468,6 +495,8 @@ int build_level_tables(ffb_ctx* c, Level& L, int W, int H, int wc, int hc) {
     return FFB_OK;
 }
 
+bool pyramid_fast_ok(int W, int H, const LevelPlan& p);
+
 int configure(ffb_ctx* c, int W, int H, int B, int maxPairs) {
     if (W < 16 || H < 16 || B < 1 || maxPairs < 1 || (double)W * H >= 4294967295.0)
         return fail(c, FFB_E_INVALID, "ffb_configure: bad geometry %dx%d batch %d pairs %d", W, H, B, maxPairs);
@@ -477,6 +506,7 @@ int configure(ffb_ctx* c, int W, int H, int B, int maxPairs) {
     free_geometry(c);
     const LevelPlan p = make_plan(W, H);
     c->W = W; c->H = H; c->B = B; c->maxPairs = maxPairs; c->nlev = p.n;
+    c->pyr_fast = pyramid_fast_ok(W, H, p);
     c->S = B + 1;
     c->ring_n = B + 8;
     size_t off = 0;
@@ -531,11 +561,61 @@ int configure(ffb_ctx* c, int W, int H, int B, int maxPairs) {
 }
 
 // ------------------------------------------------------------------ the per-batch pipeline
+// All levels in one pass when every level is an exact 2^k decimation (W, H multiples of 8).
+bool pyramid_fast_ok(int W, int H, const LevelPlan& p) {
+    static const bool generic = getenv("FFB_PYR_GENERIC") && atoi(getenv("FFB_PYR_GENERIC")) != 0;
+    if (generic || W % 8 || H % 8 || W < 64 || H < 64) return false;
+    static const int want[FFB_MAX_LEVELS] = {3, 3, 9, 19};
+    for (int l = 0; l < p.n; ++l)
+        if (p.ksize[l] != want[p.k[l]] || p.w[l] != (W >> p.k[l]) || p.h[l] != (H >> p.k[l])) return false;
+    return true;
+}
+
+// dst / dstride / dp are indexed by level k (0 = full resolution)
+int launch_pyramid_pow2(ffb_ctx* c, const uint8_t* src, size_t stride, int pitch, int W, int H, int nlev,
+                        float* const* dst, const size_t* dstride, const int* dp, int nb) {
+    FfbPyr2Args a;
+    memset(&a, 0, sizeof(a));
+    a.src = src; a.src_frame_stride = stride; a.src_pitch = pitch; a.W = W; a.H = H;
+    a.nlev = nlev;
+    a.aligned = (pitch % 4 == 0) && (stride % 4 == 0) && (((uintptr_t)src) % 4 == 0);
+    static const int ks[FFB_MAX_LEVELS] = {3, 3, 9, 19};
+    double px = 0;
+    for (int k = 0; k < nlev; ++k) {
+        a.dst[k] = dst[k]; a.dstride[k] = dstride[k]; a.dp[k] = dp[k];
+        a.taps[k] = make_taps(ks[k], k == 0 ? 0.0 : ((double)(1 << k) - 1.0) * 0.5);
+        px += (double)(W >> k) * (H >> k);
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        CK(c, cudaFuncSetAttribute(k_pyramid_pow2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PYR2_SMEM));
+        attr_set = true;
+    }
+    dim3 grid((W + PYR2_TX - 1) / PYR2_TX, (H + PYR2_TY - 1) / PYR2_TY, nb);
+    prof_begin(c, FFB_K_PYRAMID, (double)nb * ((double)W * H + 4.0 * px));
+    FFB_LAUNCH(k_pyramid_pow2, grid, dim3(256), PYR2_SMEM, c->s_comp, a);
+    prof_end(c);
+    CKL(c);
+    return FFB_OK;
+}
+
 int expand_frames(ffb_ctx* c, const uint8_t* src, size_t stride, int pitch, int nb, int first_frame) {
+    const bool fast = c->pyr_fast;
+    if (fast) {
+        float* dst[FFB_MAX_LEVELS] = {nullptr, nullptr, nullptr, nullptr};
+        size_t dstride[FFB_MAX_LEVELS] = {0, 0, 0, 0};
+        int dp[FFB_MAX_LEVELS] = {0, 0, 0, 0};
+        for (int l = 0; l < c->nlev; ++l) {
+            Level& L = c->lev[l];
+            dst[L.k] = L.I; dstride[L.k] = L.plane; dp[L.k] = L.rp;
+        }
+        TRY(launch_pyramid_pow2(c, src, stride, pitch, c->W, c->H, c->nlev, dst, dstride, dp, nb));
+    }
     for (int l = 0; l < c->nlev; ++l) {
         Level& L = c->lev[l];
-        TRY(launch_pyramid(c, src, stride, pitch, c->W, c->H, L.I, L.plane, L.rp, L.w, L.h, L.xi, L.xa, L.yi, L.ya,
-                           L.taps, L.RW, L.RH, nb));
+        if (!fast)
+            TRY(launch_pyramid(c, src, stride, pitch, c->W, c->H, L.I, L.plane, L.rp, L.w, L.h, L.xi, L.xa, L.yi, L.ya,
+                               L.taps, L.RW, L.RH, nb));
         FfbRing dst;
         dst.base = (char*)(c->R + L.r_off);
         dst.stride = c->r_slot_floats * sizeof(float);
@@ -555,18 +635,28 @@ int flow_pairs(ffb_ctx* c, int p0, int np) {
         R.first = p0 % c->S;
         R.mod = c->S;
         const size_t fstride = (size_t)L.fp * L.h;
+        // A1e: the separate up-sampling kernel is the default.  Fusing it into the first iteration
+        // (FFB_FUSE_UP=1) saves 16 B/px of traffic but measured slower on B200: the table -> coarse
+        // flow -> gather-address chain is one dependent load deeper than the prefetch distance hides.
+        static const bool fuse_up = getenv("FFB_FUSE_UP") && atoi(getenv("FFB_FUSE_UP")) != 0;
+        UpSrc up;
         const float2* fin = nullptr;
         if (l > 0) {
             Level& C = c->lev[l - 1];
-            TRY(launch_upsample(c, C.fB, (size_t)C.fp * C.h, C.fp, C.w, C.h, L.fA, fstride, L.fp, L.w, L.h, L.uxi,
-                                L.uxa, L.uyi, L.uya, np));
-            fin = L.fA;
+            if (fuse_up) {
+                up.src = C.fB; up.stride = (size_t)C.fp * C.h; up.sp = C.fp; up.wc = C.w; up.hc = C.h;
+                up.xi = L.uxi; up.xa = L.uxa; up.yi = L.uyi; up.ya = L.uya;
+            } else {
+                TRY(launch_upsample(c, C.fB, (size_t)C.fp * C.h, C.fp, C.w, C.h, L.fA, fstride, L.fp, L.w, L.h, L.uxi,
+                                    L.uxa, L.uyi, L.uya, np));
+                fin = L.fA;
+            }
         }
         FfbRing toB{(char*)L.fB, fstride * sizeof(float2), 0, 1 << 30};
         FfbRing toA{(char*)L.fA, fstride * sizeof(float2), 0, 1 << 30};
         FfbRing toRing{(char*)c->ring, c->ring_stride * sizeof(float2), p0 % c->ring_n, c->ring_n};
         const bool last = l == c->nlev - 1;
-        TRY(launch_flow_iter(c, R, L.plane, L.rp, L.w, L.h, fin, fstride, L.fp, toB, L.fp, np));
+        TRY(launch_flow_iter(c, R, L.plane, L.rp, L.w, L.h, fin, fstride, L.fp, toB, L.fp, np, &up));
         TRY(launch_flow_iter(c, R, L.plane, L.rp, L.w, L.h, L.fB, fstride, L.fp, toA, L.fp, np));
         TRY(launch_flow_iter(c, R, L.plane, L.rp, L.w, L.h, L.fA, fstride, L.fp, last ? toRing : toB, L.fp, np));
     }
@@ -983,6 +1073,19 @@ int ffb_stage_pyramid(ffb_ctx* c, const uint8_t* img, int W, int H, size_t pitch
     uint8_t* d_img; float* d_out; int *dxi, *dyi; float *dxa, *dya;
     TRY(s.alloc(c, &d_img, (size_t)W * H));
     CK(c, cudaMemcpy2D(d_img, W, img, pitch, W, H, cudaMemcpyHostToDevice));
+    if (pyramid_fast_ok(W, H, p)) {   // the production path for this geometry: all levels in one pass
+        float* dst[FFB_MAX_LEVELS] = {nullptr, nullptr, nullptr, nullptr};
+        size_t dstride[FFB_MAX_LEVELS] = {0, 0, 0, 0};
+        int dp[FFB_MAX_LEVELS] = {0, 0, 0, 0};
+        for (int k = 0; k < p.n; ++k) {
+            TRY(s.alloc(c, &dst[k], (size_t)(W >> k) * (H >> k)));
+            dp[k] = W >> k;
+        }
+        TRY(launch_pyramid_pow2(c, d_img, (size_t)W * H, W, W, H, p.n, dst, dstride, dp, 1));
+        CK(c, cudaStreamSynchronize(c->s_comp));
+        CK(c, cudaMemcpy(out, dst[level_k], (size_t)w * h * 4, cudaMemcpyDeviceToHost));
+        return FFB_OK;
+    }
     TRY(s.alloc(c, &d_out, (size_t)w * h));
     TRY(s.upload(c, &dxi, xi.data(), xi.size())); TRY(s.upload(c, &dxa, xa.data(), xa.size()));
     TRY(s.upload(c, &dyi, yi.data(), yi.size())); TRY(s.upload(c, &dya, ya.data(), ya.size()));
@@ -996,13 +1099,15 @@ int ffb_stage_polyexp(ffb_ctx* c, const float* img, int w, int h, float* out) {
     if (!c || !img || !out) return FFB_E_INVALID;
     CK(c, cudaSetDevice(c->device));
     Scratch s;
+    const int rp = ffb_round_up(w, 4);            // the kernel stores 16-byte vectors
+    const size_t plane = (size_t)rp * h;
     float *d_in, *d_out;
     TRY(s.upload(c, &d_in, img, (size_t)w * h));
-    TRY(s.alloc(c, &d_out, (size_t)5 * w * h));
+    TRY(s.alloc(c, &d_out, 5 * plane));
     FfbRing dst{(char*)d_out, 0, 0, 1};
-    TRY(launch_polyexp(c, d_in, (size_t)w * h, w, w, h, dst, (size_t)w * h, w, 1));
+    TRY(launch_polyexp(c, d_in, (size_t)w * h, w, w, h, dst, plane, rp, 1));
     CK(c, cudaStreamSynchronize(c->s_comp));
-    CK(c, cudaMemcpy(out, d_out, (size_t)5 * w * h * 4, cudaMemcpyDeviceToHost));
+    CK(c, cudaMemcpy2D(out, (size_t)w * 4, d_out, (size_t)rp * 4, (size_t)w * 4, (size_t)5 * h, cudaMemcpyDeviceToHost));
     return FFB_OK;
 }
 

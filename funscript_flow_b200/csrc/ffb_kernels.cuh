@@ -46,27 +46,37 @@ __device__ __forceinline__ unsigned long long ffb_warp_max_u64(unsigned long lon
 // ======================================================================================
 // K1  pyramid level: u8 frame -> f32 level image
 // ======================================================================================
+// out(dx,dy) = lerp_y( blur_y( lerp_x( blur_x(src) ) ) ): the Gaussian is evaluated only at the two
+// source columns / rows each bilinear output tap needs.  One CTA = one TW x TH output tile; its
+// source window is staged once in shared memory as float (border: REFLECT_101, single bounce --
+// the host guarantees radius < min(W, H)).
 struct FfbPyrArgs {
     const uint8_t* src; size_t src_frame_stride; int src_pitch; int W, H;
     float* dst; size_t dst_frame_stride; int dp; int w, h;        // strides in floats
     const int* xi; const float* xa; const int* yi; const float* ya;  // resize tables (device)
     FfbTaps taps;
-    int RWp;        // smem region row pitch (bytes)
-    int p_off;      // byte offset of the float plane P inside dynamic smem
+    int RWp;        // smem window row pitch (floats)
+    int p_off;      // float offset of the plane P inside dynamic smem
 };
 
-__device__ __forceinline__ float ffb_blur_u8(const unsigned char* row, int c, const FfbTaps& t) {
-    float s = t.k[0] * (float)row[c];
-    for (int i = 1; i <= t.r; ++i) s += t.k[i] * ((float)row[c - i] + (float)row[c + i]);
+__device__ __forceinline__ int ffb_reflect1(int i, int n) {   // BORDER_REFLECT_101, |overshoot| < n
+    i = i < 0 ? -i : i;
+    return i >= n ? 2 * n - 2 - i : i;
+}
+
+__device__ __forceinline__ float ffb_blur_row(const float* row, int c, const FfbTaps& t) {
+    float s = t.k[0] * row[c];
+    for (int i = 1; i <= t.r; ++i) s += t.k[i] * (row[c - i] + row[c + i]);
     return s;
 }
 
 template <int TW, int TH>
 __global__ void __launch_bounds__(TW* TH) k_pyramid_level(FfbPyrArgs a) {
-    FFB_DYN_SMEM(unsigned char, smem);
-    unsigned char* reg = smem;
-    float* P = reinterpret_cast<float*>(smem + a.p_off);
+    FFB_DYN_SMEM(float, smem);
+    float* reg = smem;
+    float* P = smem + a.p_off;
     const int tid = threadIdx.x;
+    const int tx = tid % TW, ty = tid / TW;
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, f = blockIdx.z;
     const int x_last = min(x0 + TW, a.w) - 1, y_last = min(y0 + TH, a.h) - 1;
     const int r = a.taps.r;
@@ -76,40 +86,36 @@ __global__ void __launch_bounds__(TW* TH) k_pyramid_level(FfbPyrArgs a) {
     const int sy_hi = min(a.yi[y_last] + 1, a.H - 1) + r;
     const int rw = sx_hi - sx_lo + 1, rh = sy_hi - sy_lo + 1;
     const uint8_t* src = a.src + (size_t)f * a.src_frame_stride;
-    // stage the source window (border handled here: REFLECT_101, like cv::GaussianBlur's default)
-    for (int i = tid; i < rw * rh; i += TW * TH) {
-        const int ry = i / rw, rx = i - ry * rw;
-        const int sy = ffb_reflect101(sy_lo + ry, a.H), sx = ffb_reflect101(sx_lo + rx, a.W);
-        reg[ry * a.RWp + rx] = src[(size_t)sy * a.src_pitch + sx];
+    for (int ry = ty; ry < rh; ry += TH) {
+        const uint8_t* srow = src + (size_t)ffb_reflect1(sy_lo + ry, a.H) * a.src_pitch;
+        float* drow = reg + ry * a.RWp;
+        for (int rx = tx; rx < rw; rx += TW) drow[rx] = (float)__ldg(srow + ffb_reflect1(sx_lo + rx, a.W));
     }
     __syncthreads();
     // pass 1: horizontal blur evaluated only at the two resize taps of each output column, lerped
-    for (int i = tid; i < rh * TW; i += TW * TH) {
-        const int ry = i / TW, ox = i - ry * TW;
-        const int dx = x0 + ox;
-        float v = 0.f;
-        if (dx < a.w) {
-            const int s0 = a.xi[dx];
-            const float al = a.xa[dx];
-            const unsigned char* row = reg + ry * a.RWp;
-            const float b0 = ffb_blur_u8(row, s0 - sx_lo, a.taps);
-            if (al != 0.f) {
-                const float b1 = ffb_blur_u8(row, min(s0 + 1, a.W - 1) - sx_lo, a.taps);
-                v = b0 * (1.f - al) + b1 * al;
-            } else {
-                v = b0;
+    {
+        const int dx = x0 + tx;
+        const bool ok = dx < a.w;
+        const int s0 = ok ? a.xi[dx] : 0;
+        const float al = ok ? a.xa[dx] : 0.f;
+        const int c0 = s0 - sx_lo, c1 = min(s0 + 1, a.W - 1) - sx_lo;
+        for (int ry = ty; ry < rh; ry += TH) {
+            float v = 0.f;
+            if (ok) {
+                const float* row = reg + ry * a.RWp;
+                v = ffb_blur_row(row, c0, a.taps);
+                if (al != 0.f) v = v * (1.f - al) + ffb_blur_row(row, c1, a.taps) * al;
             }
+            P[ry * TW + tx] = v;
         }
-        P[ry * TW + ox] = v;
     }
     __syncthreads();
     // pass 2: vertical blur at the two resize rows, lerped
-    const int ox = tid % TW, oy = tid / TW;
-    const int dx = x0 + ox, dy = y0 + oy;
+    const int dx = x0 + tx, dy = y0 + ty;
     if (dx < a.w && dy < a.h) {
         const int s0 = a.yi[dy];
         const float be = a.ya[dy];
-        const float* col = P + ox;
+        const float* col = P + tx;
         int c = s0 - sy_lo;
         float b0 = a.taps.k[0] * col[c * TW];
         for (int i = 1; i <= r; ++i) b0 += a.taps.k[i] * (col[(c - i) * TW] + col[(c + i) * TW]);
@@ -125,8 +131,116 @@ __global__ void __launch_bounds__(TW* TH) k_pyramid_level(FfbPyrArgs a) {
 }
 
 // ======================================================================================
+// K1'  all pyramid levels in one pass (frames whose width and height are multiples of 8)
+// ======================================================================================
+// With W, H divisible by 8 every level is an exact 2^k decimation: output (dx, dy) of level k lerps
+// (weights 1/2, 1/2) the blurred image at source columns 2^k dx + 2^(k-1) - 1, +1 (same for rows),
+// so a 128 x 32 source tile with an 8-pixel halo yields the 128x32, 64x16, 32x8 and 16x4 output
+// tiles of levels 0..3.  The source tile is read from HBM once (32-bit loads, converted to float in
+// shared memory) instead of once per level; the arithmetic per output is the same expression, in
+// the same order, as k_pyramid_level (the two paths agree to FMA-contraction rounding, <= 2 ulp).
+constexpr int PYR2_TX = 128, PYR2_TY = 32, PYR2_HL = 8;
+constexpr int PYR2_RW = PYR2_TX + 2 * PYR2_HL, PYR2_RH = PYR2_TY + 2 * PYR2_HL;
+constexpr size_t PYR2_SMEM = sizeof(float) * (PYR2_RW * PYR2_RH + PYR2_RH * PYR2_TX);
+
+struct FfbPyr2Args {
+    const uint8_t* src; size_t src_frame_stride; int src_pitch; int W, H;
+    float* dst[FFB_MAX_LEVELS]; size_t dstride[FFB_MAX_LEVELS]; int dp[FFB_MAX_LEVELS];   // index = level k
+    FfbTaps taps[FFB_MAX_LEVELS];
+    int nlev;
+    int aligned;     // source rows are 4-byte aligned (pitch % 4 == 0 and base % 4 == 0)
+};
+
+template <int R>
+__device__ __forceinline__ float ffb_blur_row_t(const float* row, const FfbTaps& t) {
+    float s = t.k[0] * row[0];
+#pragma unroll
+    for (int i = 1; i <= R; ++i) s += t.k[i] * (row[-i] + row[i]);
+    return s;
+}
+template <int R>
+__device__ __forceinline__ float ffb_blur_col_t(const float* col, int pitch, const FfbTaps& t) {
+    float s = t.k[0] * col[0];
+#pragma unroll
+    for (int i = 1; i <= R; ++i) s += t.k[i] * (col[-i * pitch] + col[i * pitch]);
+    return s;
+}
+
+template <int K, int R>
+__device__ __forceinline__ void ffb_pyr2_level(const FfbPyr2Args& a, const float* reg, float* P, int X0, int Y0, int f,
+                                               int tid) {
+    constexpr int OW = PYR2_TX >> K, OH = PYR2_TY >> K;
+    constexpr int OFF = K == 0 ? 0 : (1 << (K - 1)) - 1;     // first bilinear tap inside a 2^K cell
+    const FfbTaps& t = a.taps[K];
+    // pass 1: rows of the window -> P[ry][ox]
+    for (int i = tid; i < PYR2_RH * OW; i += 256) {
+        const int ry = i / OW, ox = i - ry * OW;
+        const float* row = reg + ry * PYR2_RW + (ox << K) + OFF + PYR2_HL;
+        float v = ffb_blur_row_t<R>(row, t);
+        if (K > 0) v = v * (1.f - 0.5f) + ffb_blur_row_t<R>(row + 1, t) * 0.5f;
+        P[ry * OW + ox] = v;
+    }
+    __syncthreads();
+    // pass 2
+    const int wk = a.W >> K, hk = a.H >> K;
+    float* dst = a.dst[K] + (size_t)f * a.dstride[K];
+    for (int i = tid; i < OH * OW; i += 256) {
+        const int oy = i / OW, ox = i - oy * OW;
+        const int x = (X0 >> K) + ox, y = (Y0 >> K) + oy;
+        if (x < wk && y < hk) {
+            const float* col = P + ((oy << K) + OFF + PYR2_HL) * OW + ox;
+            float v = ffb_blur_col_t<R>(col, OW, t);
+            if (K > 0) v = v * (1.f - 0.5f) + ffb_blur_col_t<R>(col + OW, OW, t) * 0.5f;
+            dst[(size_t)y * a.dp[K] + x] = v;
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) k_pyramid_pow2(FfbPyr2Args a) {
+    FFB_DYN_SMEM(float, smem);
+    float* reg = smem;                                  // [PYR2_RH][PYR2_RW]
+    float* P = smem + PYR2_RW * PYR2_RH;                // up to [PYR2_RH][PYR2_TX]
+    const int tid = threadIdx.x;
+    const int X0 = blockIdx.x * PYR2_TX, Y0 = blockIdx.y * PYR2_TY, f = blockIdx.z;
+    const uint8_t* src = a.src + (size_t)f * a.src_frame_stride;
+    const int W = a.W, H = a.H;
+    // stage the window: one 4-pixel word per thread-iteration
+    constexpr int WORDS = PYR2_RW / 4;
+    for (int i = tid; i < PYR2_RH * WORDS; i += 256) {
+        const int ry = i / WORDS, wx = i - ry * WORDS;
+        const int sy = ffb_reflect1(Y0 - PYR2_HL + ry, H);
+        const int sx = X0 - PYR2_HL + 4 * wx;
+        const uint8_t* srow = src + (size_t)sy * a.src_pitch;
+        float4 v;
+        if (a.aligned && sx >= 0 && sx + 3 < W) {
+            const unsigned u = __ldg(reinterpret_cast<const unsigned*>(srow + sx));
+            v = make_float4((float)(u & 255u), (float)((u >> 8) & 255u), (float)((u >> 16) & 255u), (float)(u >> 24));
+        } else {   // image border (REFLECT_101); far outside (only on partial tiles) is never used
+            const int n2 = 2 * W - 2;
+            int c0 = ffb_reflect1(min(sx, n2), W), c1 = ffb_reflect1(min(sx + 1, n2), W);
+            int c2 = ffb_reflect1(min(sx + 2, n2), W), c3 = ffb_reflect1(min(sx + 3, n2), W);
+            v = make_float4((float)__ldg(srow + c0), (float)__ldg(srow + c1), (float)__ldg(srow + c2), (float)__ldg(srow + c3));
+        }
+        *reinterpret_cast<float4*>(reg + ry * PYR2_RW + 4 * wx) = v;
+    }
+    __syncthreads();
+    ffb_pyr2_level<0, 1>(a, reg, P, X0, Y0, f, tid);
+    if (a.nlev > 1) ffb_pyr2_level<1, 1>(a, reg, P, X0, Y0, f, tid);
+    if (a.nlev > 2) ffb_pyr2_level<2, 4>(a, reg, P, X0, Y0, f, tid);
+    if (a.nlev > 3) ffb_pyr2_level<3, 9>(a, reg, P, X0, Y0, f, tid);
+}
+
+// ======================================================================================
 // K2  polynomial expansion: f32 image -> 5 planes (d/dy, d/dx, yy, xx, xy)
 // ======================================================================================
+// CTA = 256 threads = 128 columns x 2 row halves; it produces POLY_OW = 112 output columns (the
+// other 10 + 6 columns are the replicate-border halo / padding) x POLY_ROWS rows.
+//   phase V: each thread owns one column of one row half, loads its POLY_ROWS/2 + 10 input values
+//            (all loads issued up front) and forms the three vertical sums (g, xg, xxg along y) of
+//            every row of its half from registers -> shared rows vrow[3][POLY_ROWS][132]
+//   phase H: each task = 4 adjacent outputs of one row: 4 aligned 16-byte shared loads per vertical
+//            sum, six horizontal sums with the CPU code's symmetric pairing, 5 x 16-byte stores.
 struct FfbPolyArgs {
     const float* src; size_t src_frame_stride; int sp; int w, h;  // strides in floats
     FfbRing dst;            // per frame: 5 planes of plane floats, row pitch rp
@@ -134,64 +248,104 @@ struct FfbPolyArgs {
     FfbPolyConsts c;
 };
 
-template <int TW, int TH>
-__global__ void __launch_bounds__(TW* TH) k_polyexp(FfbPolyArgs a) {
+constexpr int POLY_OW = 112;
+constexpr int POLY_ROWS = 32;
+constexpr int POLY_VP = 132;    // shared row pitch (floats)
+constexpr size_t POLY_SMEM = sizeof(float) * 3 * POLY_ROWS * POLY_VP;
+
+__global__ void __launch_bounds__(256) k_polyexp(FfbPolyArgs a) {
     constexpr int N = FFB_POLY_N;
-    constexpr int IW = TW + 2 * N, IH = TH + 2 * N;
-    __shared__ float in[IH][IW];
-    __shared__ float vr[3][TH][IW];
+    constexpr int HR = POLY_ROWS / 2;          // rows per half
+    FFB_DYN_SMEM(float, vrow);                 // [3][POLY_ROWS][POLY_VP]
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, f = blockIdx.z;
+    const int col = tid & 127, half = tid >> 7;
+    const int x0 = blockIdx.x * POLY_OW, y0 = blockIdx.y * POLY_ROWS, f = blockIdx.z;
     const float* src = a.src + (size_t)f * a.src_frame_stride;
-    // replicate border (FarnebackPolyExp clamps rows with max/min and replicates the row buffer)
-    for (int i = tid; i < IW * IH; i += TW * TH) {
-        const int ry = i / IW, rx = i - ry * IW;
-        const int sy = ffb_clampi(y0 - N + ry, 0, a.h - 1), sx = ffb_clampi(x0 - N + rx, 0, a.w - 1);
-        in[ry][rx] = src[(size_t)sy * a.sp + sx];
+    const int w = a.w, h = a.h;
+    // ---- phase V
+    {
+        const int x = ffb_clampi(x0 - N + col, 0, w - 1);      // replicate border
+        const int yb = y0 + half * HR;
+        float win[HR + 2 * N];
+#pragma unroll
+        for (int i = 0; i < HR + 2 * N; ++i) win[i] = __ldg(src + (size_t)ffb_clampi(yb - N + i, 0, h - 1) * a.sp + x);
+#pragma unroll
+        for (int r = 0; r < HR; ++r) {
+            float t0 = win[r + N] * a.c.g[0], t1 = 0.f, t2 = 0.f;
+#pragma unroll
+            for (int k = 1; k <= N; ++k) {
+                const float up = win[r + N - k], dn = win[r + N + k];
+                const float p = up + dn;
+                t0 += a.c.g[k] * p;
+                t1 += a.c.xg[k] * (dn - up);
+                t2 += a.c.xxg[k] * p;
+            }
+            const int row = half * HR + r;
+            vrow[(0 * POLY_ROWS + row) * POLY_VP + col] = t0;
+            vrow[(1 * POLY_ROWS + row) * POLY_VP + col] = t1;
+            vrow[(2 * POLY_ROWS + row) * POLY_VP + col] = t2;
+        }
+        if (col < 4) {   // pad columns 128..131 are read (not used) by the last quad's 16-byte loads
+#pragma unroll
+            for (int r = 0; r < HR; ++r)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) vrow[(k * POLY_ROWS + half * HR + r) * POLY_VP + 128 + col] = 0.f;
+        }
     }
     __syncthreads();
-    // vertical pass: three row sums (g, xg, xxg along y), symmetric pairing as in the CPU code
-    for (int i = tid; i < TH * IW; i += TW * TH) {
-        const int oy = i / IW, cx = i - oy * IW;
-        const float c0 = in[oy + N][cx];
-        float t0 = c0 * a.c.g[0], t1 = 0.f, t2 = 0.f;
+    // ---- phase H
+    constexpr int QUADS = POLY_OW / 4;
+    float* dst0 = reinterpret_cast<float*>(ffb_ring_at(a.dst, f));
+    for (int t = tid; t < QUADS * POLY_ROWS; t += 256) {
+        const int r = t / QUADS, q = t - r * QUADS;
+        const int x = x0 + 4 * q, y = y0 + r;
+        if (x >= w || y >= h) continue;
+        float v[3][16];
 #pragma unroll
-        for (int k = 1; k <= N; ++k) {
-            const float up = in[oy + N - k][cx], dn = in[oy + N + k][cx];
-            const float p = up + dn;
-            t0 += a.c.g[k] * p;
-            t1 += a.c.xg[k] * (dn - up);
-            t2 += a.c.xxg[k] * p;
-        }
-        vr[0][oy][cx] = t0;
-        vr[1][oy][cx] = t1;
-        vr[2][oy][cx] = t2;
-    }
-    __syncthreads();
-    const int ox = tid % TW, oy = tid / TW;
-    const int x = x0 + ox, y = y0 + oy;
-    if (x < a.w && y < a.h) {
-        const float* r0 = &vr[0][oy][ox + N];
-        const float* r1 = &vr[1][oy][ox + N];
-        const float* r2 = &vr[2][oy][ox + N];
-        float b1 = r0[0] * a.c.g[0], b2 = 0.f, b3 = r1[0] * a.c.g[0], b4 = 0.f, b5 = r2[0] * a.c.g[0], b6 = 0.f;
+        for (int k = 0; k < 3; ++k) {
+            const float4* p4 = reinterpret_cast<const float4*>(vrow + (k * POLY_ROWS + r) * POLY_VP + 4 * q);
 #pragma unroll
-        for (int k = 1; k <= N; ++k) {
-            const float p = r0[k], m = r0[-k];
-            const float tg = p + m;
-            b1 += tg * a.c.g[k];
-            b4 += tg * a.c.xxg[k];
-            b2 += (p - m) * a.c.xg[k];
-            b3 += (r1[k] + r1[-k]) * a.c.g[k];
-            b6 += (r1[k] - r1[-k]) * a.c.xg[k];
-            b5 += (r2[k] + r2[-k]) * a.c.g[k];
+            for (int j = 0; j < 4; ++j) {
+                const float4 t4 = p4[j];
+                v[k][4 * j] = t4.x; v[k][4 * j + 1] = t4.y; v[k][4 * j + 2] = t4.z; v[k][4 * j + 3] = t4.w;
+            }
         }
-        float* dst = reinterpret_cast<float*>(ffb_ring_at(a.dst, f)) + (size_t)y * a.rp + x;
-        dst[0] = b3 * a.c.ig11;
-        dst[a.plane] = b2 * a.c.ig11;
-        dst[2 * a.plane] = b1 * a.c.ig03 + b5 * a.c.ig33;
-        dst[3 * a.plane] = b1 * a.c.ig03 + b4 * a.c.ig33;
-        dst[4 * a.plane] = b6 * a.c.ig55;
+        float o[5][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float* r0 = &v[0][j + N];
+            const float* r1 = &v[1][j + N];
+            const float* r2 = &v[2][j + N];
+            float b1 = r0[0] * a.c.g[0], b2 = 0.f, b3 = r1[0] * a.c.g[0], b4 = 0.f, b5 = r2[0] * a.c.g[0], b6 = 0.f;
+#pragma unroll
+            for (int k = 1; k <= N; ++k) {
+                const float pp = r0[k], mm = r0[-k];
+                const float tg = pp + mm;
+                b1 += tg * a.c.g[k];
+                b4 += tg * a.c.xxg[k];
+                b2 += (pp - mm) * a.c.xg[k];
+                b3 += (r1[k] + r1[-k]) * a.c.g[k];
+                b6 += (r1[k] - r1[-k]) * a.c.xg[k];
+                b5 += (r2[k] + r2[-k]) * a.c.g[k];
+            }
+            o[0][j] = b3 * a.c.ig11;
+            o[1][j] = b2 * a.c.ig11;
+            o[2][j] = b1 * a.c.ig03 + b5 * a.c.ig33;
+            o[3][j] = b1 * a.c.ig03 + b4 * a.c.ig33;
+            o[4][j] = b6 * a.c.ig55;
+        }
+        float* dst = dst0 + (size_t)y * a.rp + x;
+        if (x + 3 < w) {
+#pragma unroll
+            for (int c = 0; c < 5; ++c)
+                *reinterpret_cast<float4*>(dst + c * a.plane) = make_float4(o[c][0], o[c][1], o[c][2], o[c][3]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 5; ++c)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (x + j < w) dst[c * a.plane + j] = o[c][j];
+        }
     }
 }
 
@@ -312,6 +466,10 @@ struct FfbIterArgs {
     FfbRing fout; int fop;                           // flow out ring (element j), pitch in float2
     int SW;                 // output columns per strip (multiple of 4, <= NT - 14)
     int SH;                 // rows per segment
+    // A1e fused: when up_src != NULL the incoming flow is the coarser level's result, bilinearly
+    // up-sampled (cv::resize tables) and doubled on the fly instead of being read from `fin`.
+    const float2* up_src; size_t up_stride; int usp; int wc, hc;
+    const int* uxi; const float* uxa; const int* uyi; const float* uya;
 };
 
 template <int NT, int U>
@@ -393,15 +551,15 @@ __global__ void __launch_bounds__(NT) k_flow_iter(FfbIterArgs a) {
     HrowT hrow = reinterpret_cast<HrowT>(smem_f);                       // [2][U][5][HP]
     RingT ring = reinterpret_cast<RingT>(smem_f + 2 * U * 5 * HP);      // [FFB_WIN][5][NT]
     const int tid = threadIdx.x;
-    const int pair = blockIdx.z;
+    const int pair = blockIdx.x;      // fastest-varying: see the launcher
     const float* R0 = reinterpret_cast<const float*>(ffb_ring_at(a.R, pair));
     const float* R1 = reinterpret_cast<const float*>(ffb_ring_at(a.R, pair + 1));
     const float2* fin = a.fin ? a.fin + (size_t)pair * a.fin_stride : nullptr;
     float2* fout = reinterpret_cast<float2*>(ffb_ring_at(a.fout, pair));
     const int w = a.w, h = a.h;
-    const int xo0 = blockIdx.x * a.SW;
+    const int xo0 = blockIdx.y * a.SW;
     const int xc = ffb_clampi(xo0 - FFB_WIN_R + tid, 0, w - 1);
-    const int y0 = blockIdx.y * a.SH;
+    const int y0 = blockIdx.z * a.SH;
     const int y1 = min(y0 + a.SH, h);
     const int nfeed = (y1 - y0) + 2 * FFB_WIN_R;
     const int nsteps = (nfeed + U - 1) / U;
@@ -470,11 +628,30 @@ __global__ void __launch_bounds__(NT) k_flow_iter(FfbIterArgs a) {
         }
     };
 
+    const float2* ups = a.up_src ? a.up_src + (size_t)pair * a.up_stride : nullptr;
+    int ux0 = 0, ux1 = 0;
+    float ual = 0.f;
+    if (ups) {
+        ux0 = a.uxi[xc];
+        ux1 = min(ux0 + 1, a.wc - 1);
+        ual = a.uxa[xc];
+    }
     auto load_flow = [&](int s, float2 (&d)[U]) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int yc = ffb_clampi(y0 - FFB_WIN_R + s * U + u, 0, h - 1);
-            d[u] = fin ? __ldg(fin + (yc * a.fip + xc)) : make_float2(0.f, 0.f);
+            if (ups) {   // same arithmetic as k_upsample_flow
+                const int uy0 = a.uyi[yc], uy1 = min(uy0 + 1, a.hc - 1);
+                const float be = a.uya[yc];
+                const float2 p00 = __ldg(ups + (uy0 * a.usp + ux0)), p01 = __ldg(ups + (uy0 * a.usp + ux1));
+                const float2 p10 = __ldg(ups + (uy1 * a.usp + ux0)), p11 = __ldg(ups + (uy1 * a.usp + ux1));
+                const float tx = p00.x * (1.f - ual) + p01.x * ual, ty = p00.y * (1.f - ual) + p01.y * ual;
+                const float bx = p10.x * (1.f - ual) + p11.x * ual, by = p10.y * (1.f - ual) + p11.y * ual;
+                d[u].x = (tx * (1.f - be) + bx * be) * 2.f;
+                d[u].y = (ty * (1.f - be) + by * be) * 2.f;
+            } else {
+                d[u] = fin ? __ldg(fin + (yc * a.fip + xc)) : make_float2(0.f, 0.f);
+            }
         }
     };
 
