@@ -23,7 +23,9 @@ FLOW_BAD_FRACTION = 2e-3        # fraction of pixels allowed beyond 0.05 px
 NORTH_STAR_MEDIAN = 0.05
 SCALAR_RTOL = 1e-3              # north_star: per-frame scalars within 1e-3 relative
 ARGMAX_MARGIN = 1e-4            # exact (x, y) is asserted when the reference's top1-top2 gap >= this
-MEAN_MAG_RTOL = 2e-3            # a handful of border pixels flip step 6's in-bounds test (up to ~0.1 px each)
+MEAN_MAG_RTOL = 2e-3            # a handful of border pixels flip step 6's in-bounds test (up to ~0.1 px each) and
+MEAN_MAG_ATOL = 5e-4            # each flip perturbs its 15x15 blur footprint over 3 iterations (~600 px by ~1e-3..5e-2 px);
+                                # on a 128x96 frame that is ~3e-4 px of mean magnitude (profiles/r1_parity_sensitivity.txt)
 
 
 def flow_stats(a, b):
@@ -147,7 +149,7 @@ def check_golden_pairs(ctx, golden_dir, names=("a", "b", "c")):
         assert_flow_close(info["flow"], flow, f"golden pair {name}")
         assert_argmax(info["pos_center"], info["val_pos"], flow, f"golden pair {name}")
         assert info["cut"] == bool(g[f"{name}_cut"])
-        assert abs(float(info["mean_mag"]) - float(g[f"{name}_mean_mag"])) <= MEAN_MAG_RTOL * float(g[f"{name}_mean_mag"]) + 1e-7
+        assert abs(float(info["mean_mag"]) - float(g[f"{name}_mean_mag"])) <= MEAN_MAG_RTOL * float(g[f"{name}_mean_mag"]) + MEAN_MAG_ATOL
         pov = api.precompute_flow_info(p0, p1, {"pov_mode": True})
         assert tuple(pov["pos_center"]) == tuple(int(v) for v in g[f"{name}_pov_center"]) and pov["val_pos"] == 0
 
@@ -162,7 +164,7 @@ def check_golden_bracket(ctx, golden_dir, batch_frames=5):
     n = len(frames) - 1
     assert r["n_pairs"] == n
     assert np.array_equal(r["cut"], g["cut"]), "scene-cut flags differ"
-    assert np.allclose(r["mean_mag"], g["mean_mag"], rtol=MEAN_MAG_RTOL, atol=1e-7)
+    assert np.allclose(r["mean_mag"], g["mean_mag"], rtol=MEAN_MAG_RTOL, atol=MEAN_MAG_ATOL)
     import cv2
     exact = 0
     for j in range(n):
