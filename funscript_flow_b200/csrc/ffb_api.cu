@@ -376,13 +376,14 @@ int launch_upsample(ffb_ctx* c, const float2* src, size_t src_stride, int sp, in
 
 // Tunables of the fused iteration kernel (threads per CTA x rows per step, rows per segment).
 // Defaults are compiled in; FFB_ITER_CFG=NTxU and FFB_ITER_SH=rows override them for tuning runs.
-struct IterCfg { int nt, u, sh; };
+struct IterCfg { int nt, u, minb, sh; };
 IterCfg iter_cfg() {
     static IterCfg cfg = [] {
-        IterCfg c{128, 2, 120};
+        IterCfg c{128, 2, 4, 180};
         if (const char* e = getenv("FFB_ITER_CFG")) {
-            int nt = 0, u = 0;
-            if (sscanf(e, "%dx%d", &nt, &u) == 2) { c.nt = nt; c.u = u; }
+            int nt = 0, u = 0, m = 0;
+            const int got = sscanf(e, "%dx%dx%d", &nt, &u, &m);
+            if (got >= 2) { c.nt = nt; c.u = u; c.minb = got == 3 ? m : 0; }
         }
         if (const char* e = getenv("FFB_ITER_SH")) { const int v = atoi(e); if (v >= 16) c.sh = v; }
         return c;
@@ -390,7 +391,7 @@ IterCfg iter_cfg() {
     return cfg;
 }
 
-template <int NT, int U>
+template <int NT, int U, int MINB, bool HFIRST = false>
 int launch_flow_iter_t(ffb_ctx* c, FfbIterArgs a, int npairs, int sh_target, double bytes) {
     const int w = a.w, h = a.h;
     const int sw_max = (NT - 2 * FFB_WIN_R) / 4 * 4;
@@ -404,12 +405,12 @@ int launch_flow_iter_t(ffb_ctx* c, FfbIterArgs a, int npairs, int sh_target, dou
     if (nseg < 1) nseg = 1;
     a.SH = (h + nseg - 1) / nseg;
     const int gy = (h + a.SH - 1) / a.SH;
-    auto kfn = k_flow_iter<NT, U>;
+    auto kfn = k_flow_iter<NT, U, MINB, HFIRST>;
     const size_t smem = ffb_flow_iter_smem<NT, U>();
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[a.up_src ? 1 : 0]) {
         CK(c, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        attr_set[a.up_src ? 1 : 0] = true;
     }
     prof_begin(c, FFB_K_FLOW_ITER, bytes);
     // pair index varies fastest in launch order: the CTAs working on one spatial tile of consecutive
@@ -443,15 +444,23 @@ int launch_flow_iter(ffb_ctx* c, FfbRing R, size_t plane, int rp, int w, int h, 
     }
     const double bytes = (double)npairs * bpp * w * h;
     const IterCfg k = iter_cfg();
-    const int key = k.nt * 10 + k.u;
+    const int key = k.nt * 100 + k.u * 10 + k.minb;
     switch (key) {
-        case 1282: return launch_flow_iter_t<128, 2>(c, a, npairs, k.sh, bytes);
-        case 1922: return launch_flow_iter_t<192, 2>(c, a, npairs, k.sh, bytes);
-        case 1924: return launch_flow_iter_t<192, 4>(c, a, npairs, k.sh, bytes);
-        case 2562: return launch_flow_iter_t<256, 2>(c, a, npairs, k.sh, bytes);
-        case 2564: return launch_flow_iter_t<256, 4>(c, a, npairs, k.sh, bytes);
-        case 1281: return launch_flow_iter_t<128, 1>(c, a, npairs, k.sh, bytes);
-        default:   return launch_flow_iter_t<128, 4>(c, a, npairs, k.sh, bytes);
+        case 12823: return launch_flow_iter_t<128, 2, 3>(c, a, npairs, k.sh, bytes);
+        case 12825: return launch_flow_iter_t<128, 2, 5>(c, a, npairs, k.sh, bytes);
+        case 12814: return launch_flow_iter_t<128, 1, 4>(c, a, npairs, k.sh, bytes);
+        case 12815: return launch_flow_iter_t<128, 1, 5>(c, a, npairs, k.sh, bytes);
+        case 12842: return launch_flow_iter_t<128, 4, 2>(c, a, npairs, k.sh, bytes);
+        case 12843: return launch_flow_iter_t<128, 4, 3>(c, a, npairs, k.sh, bytes);
+        case 19222: return launch_flow_iter_t<192, 2, 2>(c, a, npairs, k.sh, bytes);
+        case 25622: return launch_flow_iter_t<256, 2, 2>(c, a, npairs, k.sh, bytes);
+        case 6424:  return launch_flow_iter_t<64, 2, 4>(c, a, npairs, k.sh, bytes);
+        case 6428:  return launch_flow_iter_t<64, 2, 8>(c, a, npairs, k.sh, bytes);
+        case 12826: return launch_flow_iter_t<128, 2, 4, true>(c, a, npairs, k.sh, bytes);   // "x6": horizontal first
+        case 12816: return launch_flow_iter_t<128, 1, 5, true>(c, a, npairs, k.sh, bytes);
+        case 12846: return launch_flow_iter_t<128, 4, 3, true>(c, a, npairs, k.sh, bytes);
+        case 25626: return launch_flow_iter_t<256, 2, 2, true>(c, a, npairs, k.sh, bytes);
+        default:    return launch_flow_iter_t<128, 2, 4>(c, a, npairs, k.sh, bytes);
     }
 }
 
@@ -1095,6 +1104,28 @@ int ffb_stage_pyramid(ffb_ctx* c, const uint8_t* img, int W, int H, size_t pitch
     return FFB_OK;
 }
 
+// Host-side conversion between the [5][h][w] planes of the hooks' interface and the device layout of
+// an expansion (float4 [h][rp] = channels 0..3, then float [h][rp] = channel 4).
+static void planes_to_expansion(const float* planes, int w, int h, int rp, std::vector<float>& dev) {
+    const size_t plane = (size_t)rp * h;
+    dev.assign(5 * plane, 0.f);
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            const size_t pix = (size_t)y * rp + x, src = (size_t)y * w + x;
+            for (int ch = 0; ch < 4; ++ch) dev[4 * pix + ch] = planes[(size_t)ch * w * h + src];
+            dev[4 * plane + pix] = planes[(size_t)4 * w * h + src];
+        }
+}
+static void expansion_to_planes(const std::vector<float>& dev, int w, int h, int rp, float* planes) {
+    const size_t plane = (size_t)rp * h;
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            const size_t pix = (size_t)y * rp + x, dst = (size_t)y * w + x;
+            for (int ch = 0; ch < 4; ++ch) planes[(size_t)ch * w * h + dst] = dev[4 * pix + ch];
+            planes[(size_t)4 * w * h + dst] = dev[4 * plane + pix];
+        }
+}
+
 int ffb_stage_polyexp(ffb_ctx* c, const float* img, int w, int h, float* out) {
     if (!c || !img || !out) return FFB_E_INVALID;
     CK(c, cudaSetDevice(c->device));
@@ -1107,7 +1138,9 @@ int ffb_stage_polyexp(ffb_ctx* c, const float* img, int w, int h, float* out) {
     FfbRing dst{(char*)d_out, 0, 0, 1};
     TRY(launch_polyexp(c, d_in, (size_t)w * h, w, w, h, dst, plane, rp, 1));
     CK(c, cudaStreamSynchronize(c->s_comp));
-    CK(c, cudaMemcpy2D(out, (size_t)w * 4, d_out, (size_t)rp * 4, (size_t)w * 4, (size_t)5 * h, cudaMemcpyDeviceToHost));
+    std::vector<float> host(5 * plane);
+    CK(c, cudaMemcpy(host.data(), d_out, 5 * plane * sizeof(float), cudaMemcpyDeviceToHost));
+    expansion_to_planes(host, w, h, rp, out);
     return FFB_OK;
 }
 
@@ -1138,10 +1171,11 @@ int ffb_stage_flow_iter(ffb_ctx* c, const float* R0, const float* R1, const floa
     const size_t plane = (size_t)rp * h;
     float* dR; float2 *dfi = nullptr, *dfo;
     TRY(s.alloc(c, &dR, 10 * plane));
-    for (int f = 0; f < 2; ++f)
-        for (int ch = 0; ch < 5; ++ch)
-            CK(c, cudaMemcpy2D(dR + (f * 5 + ch) * plane, (size_t)rp * 4, (f ? R1 : R0) + (size_t)ch * w * h, (size_t)w * 4,
-                               (size_t)w * 4, h, cudaMemcpyHostToDevice));
+    for (int f = 0; f < 2; ++f) {
+        std::vector<float> host;
+        planes_to_expansion(f ? R1 : R0, w, h, rp, host);
+        CK(c, cudaMemcpy(dR + (size_t)f * 5 * plane, host.data(), 5 * plane * sizeof(float), cudaMemcpyHostToDevice));
+    }
     if (flow_in) {
         TRY(s.alloc(c, &dfi, plane));
         CK(c, cudaMemcpy2D(dfi, (size_t)rp * 8, flow_in, (size_t)w * 8, (size_t)w * 8, h, cudaMemcpyHostToDevice));

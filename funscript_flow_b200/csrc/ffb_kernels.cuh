@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(256) k_pyramid_pow2(FfbPyr2Args a) {
 //            sum, six horizontal sums with the CPU code's symmetric pairing, 5 x 16-byte stores.
 struct FfbPolyArgs {
     const float* src; size_t src_frame_stride; int sp; int w, h;  // strides in floats
-    FfbRing dst;            // per frame: 5 planes of plane floats, row pitch rp
+    FfbRing dst;            // per frame-level: float4 [h][rp] (c0..c3) then float [h][rp] (c4); plane = rp * h
     size_t plane; int rp;
     FfbPolyConsts c;
 };
@@ -334,17 +334,21 @@ __global__ void __launch_bounds__(256) k_polyexp(FfbPolyArgs a) {
             o[3][j] = b1 * a.c.ig03 + b4 * a.c.ig33;
             o[4][j] = b6 * a.c.ig55;
         }
-        float* dst = dst0 + (size_t)y * a.rp + x;
+        // expansion layout: float4 (d/dy, d/dx, yy, xx) per pixel, then a separate float plane for xy
+        const size_t pix = (size_t)y * a.rp + x;
+        float4* dA = reinterpret_cast<float4*>(dst0) + pix;
+        float* dB = dst0 + 4 * a.plane + pix;
         if (x + 3 < w) {
 #pragma unroll
-            for (int c = 0; c < 5; ++c)
-                *reinterpret_cast<float4*>(dst + c * a.plane) = make_float4(o[c][0], o[c][1], o[c][2], o[c][3]);
+            for (int j = 0; j < 4; ++j) dA[j] = make_float4(o[0][j], o[1][j], o[2][j], o[3][j]);
+            *reinterpret_cast<float4*>(dB) = make_float4(o[4][0], o[4][1], o[4][2], o[4][3]);
         } else {
 #pragma unroll
-            for (int c = 0; c < 5; ++c)
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (x + j < w) dst[c * a.plane + j] = o[c][j];
+            for (int j = 0; j < 4; ++j)
+                if (x + j < w) {
+                    dA[j] = make_float4(o[0][j], o[1][j], o[2][j], o[3][j]);
+                    dB[j] = o[4][j];
+                }
         }
     }
 }
@@ -484,7 +488,11 @@ struct FfbGather {
     int inside;
 };
 
-__device__ __forceinline__ void ffb_gather_issue(const float* __restrict__ R0, const float* __restrict__ R1, int plane,
+// Expansion layout (written by k_polyexp): per frame-level a float4 image A[h][rp] holding
+// (d/dy, d/dx, yy, xx) per pixel followed by a float plane B[h][rp] holding xy.  A 2x2 bilinear
+// footprint is then 4 x 16-byte + 4 x 4-byte loads off two row addresses instead of 20 scalar loads.
+__device__ __forceinline__ void ffb_gather_issue(const float4* __restrict__ A0, const float* __restrict__ B0,
+                                                 const float4* __restrict__ A1, const float* __restrict__ B1,
                                                  int rp, int w, int h, int x, int y, float2 d, FfbGather& g) {
     float fx = (float)x + d.x, fy = (float)y + d.y;
     const float x1f = floorf(fx), y1f = floorf(fy);
@@ -495,16 +503,20 @@ __device__ __forceinline__ void ffb_gather_issue(const float* __restrict__ R0, c
     g.dy = d.y;
     g.inside = ((unsigned)x1 < (unsigned)(w - 1)) && ((unsigned)y1 < (unsigned)(h - 1));
     const int xs = min(max(x1, 0), w - 2), ys = min(max(y1, 0), h - 2);
-    const float* q = R0 + (y * rp + x);
-    const float* p = R1 + (ys * rp + xs);
-#pragma unroll
-    for (int c = 0; c < 5; ++c) {
-        g.r0[c] = __ldg(q + c * plane);
-        g.t[c][0] = __ldg(p + c * plane);
-        g.t[c][1] = __ldg(p + c * plane + 1);
-        g.t[c][2] = __ldg(p + c * plane + rp);
-        g.t[c][3] = __ldg(p + c * plane + rp + 1);
-    }
+    const unsigned o0 = (unsigned)(y * rp + x), o1 = (unsigned)(ys * rp + xs);
+    const float4 q = __ldg(A0 + o0);
+    const float q4 = __ldg(B0 + o0);
+    const float4 t00 = __ldg(A1 + o1), t01 = __ldg(A1 + o1 + 1);
+    const float4 t10 = __ldg(A1 + o1 + rp), t11 = __ldg(A1 + o1 + rp + 1);
+    g.r0[0] = q.x; g.r0[1] = q.y; g.r0[2] = q.z; g.r0[3] = q.w; g.r0[4] = q4;
+    g.t[0][0] = t00.x; g.t[0][1] = t01.x; g.t[0][2] = t10.x; g.t[0][3] = t11.x;
+    g.t[1][0] = t00.y; g.t[1][1] = t01.y; g.t[1][2] = t10.y; g.t[1][3] = t11.y;
+    g.t[2][0] = t00.z; g.t[2][1] = t01.z; g.t[2][2] = t10.z; g.t[2][3] = t11.z;
+    g.t[3][0] = t00.w; g.t[3][1] = t01.w; g.t[3][2] = t10.w; g.t[3][3] = t11.w;
+    g.t[4][0] = __ldg(B1 + o1);
+    g.t[4][1] = __ldg(B1 + o1 + 1);
+    g.t[4][2] = __ldg(B1 + o1 + rp);
+    g.t[4][3] = __ldg(B1 + o1 + rp + 1);
 }
 
 __device__ __forceinline__ void ffb_gather_finish(const FfbGather& g, int w, int h, int x, int y, float m[5]) {
@@ -541,8 +553,8 @@ __device__ __forceinline__ void ffb_gather_finish(const FfbGather& g, int w, int
     m[4] = r6 * r2 + r5 * r3;
 }
 
-template <int NT, int U>
-__global__ void __launch_bounds__(NT) k_flow_iter(FfbIterArgs a) {
+template <int NT, int U, int MINB, bool HFIRST>
+__global__ void __launch_bounds__(NT, MINB) k_flow_iter(FfbIterArgs a) {
     constexpr int HP = NT + 4;
     // dynamic shared memory (exceeds the 48 KB static limit): hrow first (16-byte aligned), then ring
     FFB_DYN_SMEM(float, smem_f);
@@ -552,8 +564,10 @@ __global__ void __launch_bounds__(NT) k_flow_iter(FfbIterArgs a) {
     RingT ring = reinterpret_cast<RingT>(smem_f + 2 * U * 5 * HP);      // [FFB_WIN][5][NT]
     const int tid = threadIdx.x;
     const int pair = blockIdx.x;      // fastest-varying: see the launcher
-    const float* R0 = reinterpret_cast<const float*>(ffb_ring_at(a.R, pair));
-    const float* R1 = reinterpret_cast<const float*>(ffb_ring_at(a.R, pair + 1));
+    const float4* A0 = reinterpret_cast<const float4*>(ffb_ring_at(a.R, pair));
+    const float4* A1 = reinterpret_cast<const float4*>(ffb_ring_at(a.R, pair + 1));
+    const float* B0 = reinterpret_cast<const float*>(A0 + a.plane);
+    const float* B1 = reinterpret_cast<const float*>(A1 + a.plane);
     const float2* fin = a.fin ? a.fin + (size_t)pair * a.fin_stride : nullptr;
     float2* fout = reinterpret_cast<float2*>(ffb_ring_at(a.fout, pair));
     const int w = a.w, h = a.h;
@@ -613,7 +627,9 @@ __global__ void __launch_bounds__(NT) k_flow_iter(FfbIterArgs a) {
             const float wq = g12 * g12;
             const float e = __fmaf_rn(-g12, g12, wq);
             const float fd = __fmaf_rn(g11, g22, -wq);
-            const float idet = 1.f / ((fd + e) + 1e-3f);
+            const float den = (fd + e) + 1e-3f;
+            float idet = __fdividef(1.f, den);              // approximate reciprocal ...
+            idet = idet * __fmaf_rn(-den, idet, 2.f);       // ... plus one Newton step (<= 1 ulp, no slow path)
             o[j].x = (g11 * h2 - g12 * h1) * idet;
             o[j].y = (g22 * h1 - g12 * h2) * idet;
         }
@@ -628,7 +644,7 @@ __global__ void __launch_bounds__(NT) k_flow_iter(FfbIterArgs a) {
         }
     };
 
-    const float2* ups = a.up_src ? a.up_src + (size_t)pair * a.up_stride : nullptr;
+    const float2* ups = (a.up_src) ? a.up_src + (size_t)pair * a.up_stride : nullptr;
     int ux0 = 0, ux1 = 0;
     float ual = 0.f;
     if (ups) {
@@ -659,16 +675,19 @@ __global__ void __launch_bounds__(NT) k_flow_iter(FfbIterArgs a) {
     load_flow(0, d);
     for (int s = 0; s < nsteps; ++s) {
         const int buf = s & 1;
-        // ---- issue the gather of step s (25*U independent loads), then the flow prefetch of step s+1
+        // HFIRST: run the horizontal phase of the previous step before issuing this step's loads
+        // (lower register pressure, relies on the other resident warps to cover the load latency)
+        if (HFIRST && s > 0) horizontal(s - 1, buf ^ 1);
+        // ---- issue the gather of step s (10*U independent loads), then the flow prefetch of step s+1
         FfbGather g[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int yc = ffb_clampi(y0 - FFB_WIN_R + s * U + u, 0, h - 1);
-            ffb_gather_issue(R0, R1, a.plane, a.rp, w, h, xc, yc, d[u], g[u]);
+            ffb_gather_issue(A0, B0, A1, B1, a.rp, w, h, xc, yc, d[u], g[u]);
         }
         load_flow(s + 1, dn);
         // ---- while those are in flight: horizontal phase of the previous step
-        if (s > 0) horizontal(s - 1, buf ^ 1);
+        if (!HFIRST && s > 0) horizontal(s - 1, buf ^ 1);
         // ---- matrices + vertical running sums (Kahan-compensated add of  new - leaving)
 #pragma unroll
         for (int u = 0; u < U; ++u) {
