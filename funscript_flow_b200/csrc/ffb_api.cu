@@ -401,7 +401,12 @@ int launch_flow_iter_t(ffb_ctx* c, FfbIterArgs a, int npairs, int sh_target, dou
     const int gx = (w + a.SW - 1) / a.SW;
     // Row segments depend on the level geometry only (never on the batch composition), so a pair's
     // result is bit-identical however frames are batched or sharded.
-    int nseg = (h + sh_target / 2) / sh_target;
+    // at most sh_target rows per segment, at least min_seg segments per level (coarse levels would
+    // otherwise be a handful of long, latency-bound marches), never under 32 rows
+    static const int min_seg = getenv("FFB_ITER_MINSEG") ? atoi(getenv("FFB_ITER_MINSEG")) : 6;
+    int nseg = (h + sh_target - 1) / sh_target;
+    if (nseg < min_seg) nseg = min_seg;
+    if (nseg > (h + 31) / 32) nseg = (h + 31) / 32;
     if (nseg < 1) nseg = 1;
     a.SH = (h + nseg - 1) / nseg;
     const int gy = (h + a.SH - 1) / a.SH;
@@ -516,7 +521,7 @@ int configure(ffb_ctx* c, int W, int H, int B, int maxPairs) {
     const LevelPlan p = make_plan(W, H);
     c->W = W; c->H = H; c->B = B; c->maxPairs = maxPairs; c->nlev = p.n;
     c->pyr_fast = pyramid_fast_ok(W, H, p);
-    c->S = B + 1;
+    c->S = B + 2;      // the first batch of a bracket may carry B + 1 frames (= B pairs)
     c->ring_n = B + 8;
     size_t off = 0;
     for (int l = 0; l < p.n; ++l) {
@@ -530,7 +535,7 @@ int configure(ffb_ctx* c, int W, int H, int B, int maxPairs) {
         off = (off + 63) / 64 * 64;
         L.taps = make_taps(L.ksize, L.sigma);
         TRY(build_level_tables(c, L, W, H, l > 0 ? c->lev[l - 1].w : 0, l > 0 ? c->lev[l - 1].h : 0));
-        TRY(dev_alloc(c, &L.I, (size_t)B * L.plane));
+        TRY(dev_alloc(c, &L.I, (size_t)(B + 1) * L.plane));
         if (l < p.n - 1 || true) {
             TRY(dev_alloc(c, &L.fA, (size_t)B * L.fp * L.h));
             TRY(dev_alloc(c, &L.fB, (size_t)B * L.fp * L.h));
@@ -543,10 +548,10 @@ int configure(ffb_ctx* c, int W, int H, int B, int maxPairs) {
     TRY(dev_alloc(c, &c->ring, (size_t)c->ring_n * c->ring_stride));
     const size_t fbytes = (size_t)W * H;
     for (int b = 0; b < 2; ++b) {
-        TRY(dev_alloc(c, &c->d_u8[b], (size_t)B * fbytes));
+        TRY(dev_alloc(c, &c->d_u8[b], (size_t)(B + 1) * fbytes));
         void* hp = nullptr;
-        if (cudaHostAlloc(&hp, (size_t)B * fbytes, cudaHostAllocDefault) != cudaSuccess)
-            return fail(c, FFB_E_NOMEM, "cudaHostAlloc(%zu) failed", (size_t)B * fbytes);
+        if (cudaHostAlloc(&hp, (size_t)(B + 1) * fbytes, cudaHostAllocDefault) != cudaSuccess)
+            return fail(c, FFB_E_NOMEM, "cudaHostAlloc(%zu) failed", (size_t)(B + 1) * fbytes);
         c->h_pin[b] = (uint8_t*)hp;
     }
     TRY(dev_alloc(c, &c->d_cx, (size_t)maxPairs)); TRY(dev_alloc(c, &c->d_cy, (size_t)maxPairs));
@@ -898,7 +903,10 @@ int ffb_bracket_push(ffb_ctx* c, const uint8_t* frames, int n, size_t pitch, siz
         return fail(c, FFB_E_INVALID, "ffb_bracket_push: bad arguments");
     const PtrKind kind = classify(frames);
     for (int i = 0; i < n;) {
-        const int nb = n - i < c->B ? n - i : c->B;
+        // a bracket of k*B pairs has k*B + 1 frames: let its first batch take B + 1 frames (B pairs)
+        // so that no degenerate one-frame batch is left over
+        const int cap = c->frames_seen == 0 ? c->B + 1 : c->B;
+        const int nb = n - i < cap ? n - i : cap;
         TRY(process_batch(c, frames + (size_t)i * stride, nb, pitch, stride, kind));
         i += nb;
     }
