@@ -201,7 +201,7 @@ struct ffb_ctx {
     double *d_centers = nullptr, *d_scalar = nullptr;
     unsigned long long* d_pkey = nullptr;
     double *d_psum = nullptr, *d_rpart = nullptr;
-    int div_nblk = 0, div_rpb = 0, rad_gx = 0, rad_gy = 0, rad_rpb = 0;
+    int div_nblk = 0, div_rpb = 0, div_gx = 0, div_gy = 0, rad_gx = 0, rad_gy = 0, rad_rpb = 0;
     char* h_res = nullptr;    // pinned result staging
     // bracket state
     bool in_bracket = false;
@@ -379,7 +379,7 @@ int launch_upsample(ffb_ctx* c, const float2* src, size_t src_stride, int sp, in
 struct IterCfg { int nt, u, minb, sh; };
 IterCfg iter_cfg() {
     static IterCfg cfg = [] {
-        IterCfg c{128, 2, 4, 180};
+        IterCfg c{128, 2, 6, 180};
         if (const char* e = getenv("FFB_ITER_CFG")) {
             int nt = 0, u = 0, m = 0;
             const int got = sscanf(e, "%dx%dx%d", &nt, &u, &m);
@@ -410,7 +410,7 @@ int launch_flow_iter_t(ffb_ctx* c, FfbIterArgs a, int npairs, int sh_target, dou
     if (nseg < 1) nseg = 1;
     a.SH = (h + nseg - 1) / nseg;
     const int gy = (h + a.SH - 1) / a.SH;
-    auto kfn = k_flow_iter<NT, U, MINB, HFIRST>;
+    auto kfn = a.up_src ? k_flow_iter<NT, U, MINB, HFIRST, true> : k_flow_iter<NT, U, MINB, HFIRST, false>;
     const size_t smem = ffb_flow_iter_smem<NT, U>();
     static bool attr_set[2] = {false, false};
     if (!attr_set[a.up_src ? 1 : 0]) {
@@ -429,7 +429,6 @@ int launch_flow_iter_t(ffb_ctx* c, FfbIterArgs a, int npairs, int sh_target, dou
 
 struct UpSrc {   // coarser-level flow to be up-sampled inside the iteration kernel (A1e fused)
     const float2* src = nullptr; size_t stride = 0; int sp = 0, wc = 0, hc = 0;
-    const int *xi = nullptr, *yi = nullptr; const float *xa = nullptr, *ya = nullptr;
 };
 
 int launch_flow_iter(ffb_ctx* c, FfbRing R, size_t plane, int rp, int w, int h, const float2* fin, size_t fin_stride,
@@ -439,11 +438,9 @@ int launch_flow_iter(ffb_ctx* c, FfbRing R, size_t plane, int rp, int w, int h, 
     a.fin = fin; a.fin_stride = fin_stride; a.fip = fip; a.fout = fout; a.fop = fop;
     a.SW = a.SH = 0;
     a.up_src = nullptr; a.up_stride = 0; a.usp = a.wc = a.hc = 0;
-    a.uxi = a.uyi = nullptr; a.uxa = a.uya = nullptr;
     double bpp = fin ? 56.0 : 48.0;
     if (up && up->src) {
         a.up_src = up->src; a.up_stride = up->stride; a.usp = up->sp; a.wc = up->wc; a.hc = up->hc;
-        a.uxi = up->xi; a.uxa = up->xa; a.uyi = up->yi; a.uya = up->ya;
         a.fin = nullptr;
         bpp = 48.0 + 8.0 * ((double)up->wc * up->hc) / ((double)w * h);
     }
@@ -465,7 +462,8 @@ int launch_flow_iter(ffb_ctx* c, FfbRing R, size_t plane, int rp, int w, int h, 
         case 12816: return launch_flow_iter_t<128, 1, 5, true>(c, a, npairs, k.sh, bytes);
         case 12846: return launch_flow_iter_t<128, 4, 3, true>(c, a, npairs, k.sh, bytes);
         case 25626: return launch_flow_iter_t<256, 2, 2, true>(c, a, npairs, k.sh, bytes);
-        default:    return launch_flow_iter_t<128, 2, 4>(c, a, npairs, k.sh, bytes);
+        case 12824: return launch_flow_iter_t<128, 2, 4>(c, a, npairs, k.sh, bytes);
+        default:    return launch_flow_iter_t<128, 2, 4, true>(c, a, npairs, k.sh, bytes);   // 128x2, horizontal first
     }
 }
 
@@ -560,7 +558,9 @@ int configure(ffb_ctx* c, int W, int H, int B, int maxPairs) {
     TRY(dev_alloc(c, &c->d_centers, (size_t)2 * maxPairs)); TRY(dev_alloc(c, &c->d_scalar, (size_t)maxPairs));
     // reduction geometry: fixed per configuration so results do not depend on batch composition
     c->div_rpb = 8;
-    c->div_nblk = (H + c->div_rpb - 1) / c->div_rpb;
+    c->div_gx = (H + c->div_rpb - 1) / c->div_rpb;
+    c->div_gy = 1;
+    c->div_nblk = c->div_gx;
     c->rad_gx = (W + 255) / 256;
     c->rad_rpb = 32;
     c->rad_gy = (H + c->rad_rpb - 1) / c->rad_rpb;
@@ -649,17 +649,16 @@ int flow_pairs(ffb_ctx* c, int p0, int np) {
         R.first = p0 % c->S;
         R.mod = c->S;
         const size_t fstride = (size_t)L.fp * L.h;
-        // A1e: the separate up-sampling kernel is the default.  Fusing it into the first iteration
-        // (FFB_FUSE_UP=1) saves 16 B/px of traffic but measured slower on B200: the table -> coarse
-        // flow -> gather-address chain is one dependent load deeper than the prefetch distance hides.
-        static const bool fuse_up = getenv("FFB_FUSE_UP") && atoi(getenv("FFB_FUSE_UP")) != 0;
+        // A1e: fused into the first iteration when the level is an exact 2:1 refinement of the coarser
+        // one (closed-form resize taps, no table in the address chain); otherwise the table-driven
+        // k_upsample_flow runs first.  FFB_FUSE_UP=0 forces the separate kernel.
+        static const bool fuse_up = !(getenv("FFB_FUSE_UP") && atoi(getenv("FFB_FUSE_UP")) == 0);
         UpSrc up;
         const float2* fin = nullptr;
         if (l > 0) {
             Level& C = c->lev[l - 1];
-            if (fuse_up) {
+            if (fuse_up && L.w == 2 * C.w && L.h == 2 * C.h) {
                 up.src = C.fB; up.stride = (size_t)C.fp * C.h; up.sp = C.fp; up.wc = C.w; up.hc = C.h;
-                up.xi = L.uxi; up.xa = L.uxa; up.yi = L.uyi; up.ya = L.uya;
             } else {
                 TRY(launch_upsample(c, C.fB, (size_t)C.fp * C.h, C.fp, C.w, C.h, L.fA, fstride, L.fp, L.w, L.h, L.uxi,
                                     L.uxa, L.uyi, L.uya, np));
@@ -683,7 +682,7 @@ int phase1_reduce(ffb_ctx* c, int p0, int np) {
     d.fp = c->fp0; d.w = c->W; d.h = c->H; d.rows_per_block = c->div_rpb;
     d.pkey = c->d_pkey; d.psum = c->d_psum;
     prof_begin(c, FFB_K_DIVMAG, (double)np * 8.0 * c->W * c->H);
-    FFB_LAUNCH(k_divmag, dim3(c->div_nblk, 1, np), dim3(256), 0, c->s_comp, d);
+    FFB_LAUNCH(k_divmag, dim3(c->div_gx, c->div_gy, np), dim3(256), 0, c->s_comp, d);
     prof_end(c);
     CKL(c);
     FfbP1Args f;

@@ -470,10 +470,9 @@ struct FfbIterArgs {
     FfbRing fout; int fop;                           // flow out ring (element j), pitch in float2
     int SW;                 // output columns per strip (multiple of 4, <= NT - 14)
     int SH;                 // rows per segment
-    // A1e fused: when up_src != NULL the incoming flow is the coarser level's result, bilinearly
-    // up-sampled (cv::resize tables) and doubled on the fly instead of being read from `fin`.
+    // A1e fused (exact 2:1 levels only): when up_src != NULL the incoming flow is the coarser level's
+    // result, up-sampled and doubled on the fly instead of being read from `fin`.
     const float2* up_src; size_t up_stride; int usp; int wc, hc;
-    const int* uxi; const float* uxa; const int* uyi; const float* uya;
 };
 
 template <int NT, int U>
@@ -553,7 +552,16 @@ __device__ __forceinline__ void ffb_gather_finish(const FfbGather& g, int w, int
     m[4] = r6 * r2 + r5 * r3;
 }
 
-template <int NT, int U, int MINB, bool HFIRST>
+// cv::resize(INTER_LINEAR) source index / weight for an exact 2:1 up-sampling (dst_n == 2 * src_n)
+__device__ __forceinline__ void ffb_up2(int d, int src_n, int& i0, int& i1, float& al) {
+    i0 = (d - 1) >> 1;                 // d = 0 -> -1
+    al = (d & 1) ? 0.25f : 0.75f;
+    if (i0 < 0) { i0 = 0; al = 0.f; }
+    if (i0 >= src_n - 1) { i0 = src_n - 1; al = 0.f; }
+    i1 = min(i0 + 1, src_n - 1);
+}
+
+template <int NT, int U, int MINB, bool HFIRST, bool UP2X>
 __global__ void __launch_bounds__(NT, MINB) k_flow_iter(FfbIterArgs a) {
     constexpr int HP = NT + 4;
     // dynamic shared memory (exceeds the 48 KB static limit): hrow first (16-byte aligned), then ring
@@ -644,21 +652,22 @@ __global__ void __launch_bounds__(NT, MINB) k_flow_iter(FfbIterArgs a) {
         }
     };
 
-    const float2* ups = (a.up_src) ? a.up_src + (size_t)pair * a.up_stride : nullptr;
+    // A1e fused (UP2X): the incoming flow is the coarser level's result, bilinearly up-sampled and
+    // doubled on the fly.  Only instantiated for exact 2:1 level geometry, where cv::resize's table is
+    // closed-form: output d reads source (d-1)>>1 (+1) with weight 0.75 (d even) / 0.25 (d odd),
+    // clamped at both ends -- no table loads in the address chain.
+    const float2* ups = UP2X ? a.up_src + (size_t)pair * a.up_stride : nullptr;
     int ux0 = 0, ux1 = 0;
     float ual = 0.f;
-    if (ups) {
-        ux0 = a.uxi[xc];
-        ux1 = min(ux0 + 1, a.wc - 1);
-        ual = a.uxa[xc];
-    }
+    if (UP2X) ffb_up2(xc, a.wc, ux0, ux1, ual);
     auto load_flow = [&](int s, float2 (&d)[U]) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int yc = ffb_clampi(y0 - FFB_WIN_R + s * U + u, 0, h - 1);
-            if (ups) {   // same arithmetic as k_upsample_flow
-                const int uy0 = a.uyi[yc], uy1 = min(uy0 + 1, a.hc - 1);
-                const float be = a.uya[yc];
+            if (UP2X) {   // same arithmetic as k_upsample_flow
+                int uy0, uy1;
+                float be;
+                ffb_up2(yc, a.hc, uy0, uy1, be);
                 const float2 p00 = __ldg(ups + (uy0 * a.usp + ux0)), p01 = __ldg(ups + (uy0 * a.usp + ux1));
                 const float2 p10 = __ldg(ups + (uy1 * a.usp + ux0)), p11 = __ldg(ups + (uy1 * a.usp + ux1));
                 const float tx = p00.x * (1.f - ual) + p01.x * ual, ty = p00.y * (1.f - ual) + p01.y * ual;
@@ -867,6 +876,7 @@ __global__ void __launch_bounds__(256) k_radial(FfbRadArgs a) {
         const double wxd = a.pov ? 1.0 : (((double)x > cx) ? (double)(w - x) / (double)w : (double)x / (double)w);
         const float wx = (float)wxd;
         const float ax = (float)(wxd * ((double)x - cx));
+#pragma unroll 8
         for (int y = ylo; y < yhi; ++y) {
             const float2 f = __ldg(F + (size_t)y * a.fp + x);
             const double wy = a.pov ? 1.0 : (((double)y > cy) ? (double)(h - y) / (double)h : (double)y / (double)h);

@@ -199,6 +199,10 @@ template <class T> static inline T __shfl_down_sync(unsigned, T v, int d) {
     int lane = emu::g_cur->linear % 32;
     return emu::shfl_generic(v, lane + d < 32 ? lane + d : lane);
 }
+template <class T> static inline T __shfl_up_sync(unsigned, T v, int d) {
+    int lane = emu::g_cur->linear % 32;
+    return emu::shfl_generic(v, lane - d >= 0 ? lane - d : lane);
+}
 template <class T> static inline T __shfl_sync(unsigned, T v, int l) { return emu::shfl_generic(v, l); }
 
 // ------------------------------------------------------------------ intrinsics
