@@ -243,6 +243,15 @@ def main():
         it = stats["flow_iter"]
         achieved = it["alg_bytes"] / (it["ms"] / 1000.0) / 1e9 if it["ms"] > 0 else 0.0
         kernel_ms = {k: round(v["ms"] / args.steps, 4) for k, v in stats.items()}
+        traffic, traffic_note = None, None
+        try:   # DRAM bytes of the dominant launch shape from the committed ncu --set full capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+            if (W, H) == (1920, 1080):
+                traffic = tj["traffic"]
+                traffic_note = (f"{tj['launch_shape']}: dram read+write {tj['traffic'] / 1e9:.3f} GB vs algorithmic "
+                                f"{tj['alg_bytes_per_launch'] / 1e9:.3f} GB per launch ({tj['source']})")
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -255,7 +264,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_flow_iter", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
+                         "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
                          "alg_bytes_per_launch": it["alg_bytes"] / max(1, it["launches"]),
                          "avg_launch_ms": it["ms"] / max(1, it["launches"]), "launches": it["launches"],
                          "whole_path_bytes_per_pair": 269.7 * W * H,
