@@ -391,12 +391,12 @@ IterCfg iter_cfg() {
     return cfg;
 }
 
-template <int NT, int U, int MINB, bool HFIRST = false>
+template <int NT, int U, int MINB, bool HFIRST = false, int HO = 4>
 int launch_flow_iter_t(ffb_ctx* c, FfbIterArgs a, int npairs, int sh_target, double bytes) {
     const int w = a.w, h = a.h;
-    const int sw_max = (NT - 2 * FFB_WIN_R) / 4 * 4;
+    const int sw_max = (NT - 2 * FFB_WIN_R) / HO * HO;
     const int nstrips = (w + sw_max - 1) / sw_max;
-    a.SW = ffb_round_up((w + nstrips - 1) / nstrips, 4);
+    a.SW = ffb_round_up((w + nstrips - 1) / nstrips, HO);
     if (a.SW > sw_max) a.SW = sw_max;
     const int gx = (w + a.SW - 1) / a.SW;
     // Row segments depend on the level geometry only (never on the batch composition), so a pair's
@@ -410,7 +410,7 @@ int launch_flow_iter_t(ffb_ctx* c, FfbIterArgs a, int npairs, int sh_target, dou
     if (nseg < 1) nseg = 1;
     a.SH = (h + nseg - 1) / nseg;
     const int gy = (h + a.SH - 1) / a.SH;
-    auto kfn = a.up_src ? k_flow_iter<NT, U, MINB, HFIRST, true> : k_flow_iter<NT, U, MINB, HFIRST, false>;
+    auto kfn = a.up_src ? k_flow_iter<NT, U, MINB, HFIRST, true, HO> : k_flow_iter<NT, U, MINB, HFIRST, false, HO>;
     const size_t smem = ffb_flow_iter_smem<NT, U>();
     static bool attr_set[2] = {false, false};
     if (!attr_set[a.up_src ? 1 : 0]) {
@@ -463,6 +463,9 @@ int launch_flow_iter(ffb_ctx* c, FfbRing R, size_t plane, int rp, int w, int h, 
         case 12846: return launch_flow_iter_t<128, 4, 3, true>(c, a, npairs, k.sh, bytes);
         case 25626: return launch_flow_iter_t<256, 2, 2, true>(c, a, npairs, k.sh, bytes);
         case 12824: return launch_flow_iter_t<128, 2, 4>(c, a, npairs, k.sh, bytes);
+        case 12827: return launch_flow_iter_t<128, 2, 4, true, 8>(c, a, npairs, k.sh, bytes);   // "x7": hfirst, 8 outputs/task
+        case 12847: return launch_flow_iter_t<128, 4, 3, true, 8>(c, a, npairs, k.sh, bytes);
+        case 25627: return launch_flow_iter_t<256, 2, 2, true, 8>(c, a, npairs, k.sh, bytes);
         default:    return launch_flow_iter_t<128, 2, 4, true>(c, a, npairs, k.sh, bytes);   // 128x2, horizontal first
     }
 }
@@ -904,7 +907,10 @@ int ffb_bracket_push(ffb_ctx* c, const uint8_t* frames, int n, size_t pitch, siz
     for (int i = 0; i < n;) {
         // a bracket of k*B pairs has k*B + 1 frames: let its first batch take B + 1 frames (B pairs)
         // so that no degenerate one-frame batch is left over
-        const int cap = c->frames_seen == 0 ? c->B + 1 : c->B;
+        int cap = c->frames_seen == 0 ? c->B + 1 : c->B;
+        // host input: keep the first batch of a bracket small so that compute starts after a short
+        // upload and every later upload hides behind the previous batch's kernels
+        if (c->frames_seen == 0 && kind != PTR_DEVICE && c->B >= 8) cap = c->B / 4 + 1;
         const int nb = n - i < cap ? n - i : cap;
         TRY(process_batch(c, frames + (size_t)i * stride, nb, pitch, stride, kind));
         i += nb;

@@ -561,8 +561,9 @@ __device__ __forceinline__ void ffb_up2(int d, int src_n, int& i0, int& i1, floa
     i1 = min(i0 + 1, src_n - 1);
 }
 
-template <int NT, int U, int MINB, bool HFIRST, bool UP2X>
+template <int NT, int U, int MINB, bool HFIRST, bool UP2X, int HO>
 __global__ void __launch_bounds__(NT, MINB) k_flow_iter(FfbIterArgs a) {
+    static_assert(HO == 4 || HO == 8, "outputs per horizontal task");
     constexpr int HP = NT + 4;
     // dynamic shared memory (exceeds the 48 KB static limit): hrow first (16-byte aligned), then ring
     FFB_DYN_SMEM(float, smem_f);
@@ -585,12 +586,12 @@ __global__ void __launch_bounds__(NT, MINB) k_flow_iter(FfbIterArgs a) {
     const int y1 = min(y0 + a.SH, h);
     const int nfeed = (y1 - y0) + 2 * FFB_WIN_R;
     const int nsteps = (nfeed + U - 1) / U;
-    const int groups = a.SW >> 2;
+    const int groups = a.SW / HO;
     // horizontal-phase role of this thread (fixed for the whole kernel)
     const bool hz = tid < U * groups;
     const int hu = hz ? tid / groups : 0;
     const int hg = hz ? tid - hu * groups : 0;
-    const int hx = xo0 + 4 * hg;
+    const int hx = xo0 + HO * hg;
 
 #pragma unroll
     for (int s = 0; s < FFB_WIN; ++s)
@@ -612,6 +613,58 @@ __global__ void __launch_bounds__(NT, MINB) k_flow_iter(FfbIterArgs a) {
         const int i = s * U + hu;
         if (!hz || i < 2 * FFB_WIN_R || i >= nfeed || hx >= w) return;
         const int yo = y0 + i - 2 * FFB_WIN_R;
+        if (HO == 8) {
+            // 8 adjacent outputs per task: 22 window elements from six 16-byte shared loads per channel;
+            // sum_j = (e7..e14) + (e_j..e6) + (e15..e_{14+j})
+            float sum8[5][8];
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+                const float4* hp = reinterpret_cast<const float4*>(&hrow[buf][hu][c][8 * hg]);
+                const float4 q0 = hp[0], q1 = hp[1], q2 = hp[2], q3 = hp[3], q4 = hp[4], q5 = hp[5];
+                const float e[24] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w,
+                                     q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, q4.z, q4.w, q5.x, q5.y, q5.z, q5.w};
+                const float common = ((e[7] + e[8]) + (e[9] + e[10])) + ((e[11] + e[12]) + (e[13] + e[14]));
+                float L[8], R[8];
+                L[7] = 0.f;
+                L[6] = e[6];
+#pragma unroll
+                for (int j = 5; j >= 0; --j) L[j] = e[j] + L[j + 1];
+                R[0] = 0.f;
+                R[1] = e[15];
+#pragma unroll
+                for (int j = 2; j < 8; ++j) R[j] = R[j - 1] + e[14 + j];
+                sum8[c][0] = common + L[0];
+                sum8[c][7] = common + R[7];
+#pragma unroll
+                for (int j = 1; j < 7; ++j) sum8[c][j] = common + (L[j] + R[j]);
+            }
+            float2 o8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float sc = 1.f / (float)(FFB_WIN * FFB_WIN);
+                const float g11 = sum8[0][j] * sc, g12 = sum8[1][j] * sc, g22 = sum8[2][j] * sc;
+                const float h1 = sum8[3][j] * sc, h2 = sum8[4][j] * sc;
+                const float wq = g12 * g12;
+                const float e2 = __fmaf_rn(-g12, g12, wq);
+                const float fd = __fmaf_rn(g11, g22, -wq);
+                const float den = (fd + e2) + 1e-3f;
+                float idet = __fdividef(1.f, den);
+                idet = idet * __fmaf_rn(-den, idet, 2.f);
+                o8[j].x = (g11 * h2 - g12 * h1) * idet;
+                o8[j].y = (g22 * h1 - g12 * h2) * idet;
+            }
+            float2* dst8 = fout + (yo * a.fop + hx);
+            if (hx + 7 < w) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    reinterpret_cast<float4*>(dst8)[j] = make_float4(o8[2 * j].x, o8[2 * j].y, o8[2 * j + 1].x, o8[2 * j + 1].y);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (hx + j < w) dst8[j] = o8[j];
+            }
+            return;
+        }
         float sum[5][4];
 #pragma unroll
         for (int c = 0; c < 5; ++c) {

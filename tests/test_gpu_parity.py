@@ -74,6 +74,24 @@ def test_bracket_vs_oracle_640x360(gpu_ctx):
         assert np.allclose(r["scalar"], vals, rtol=pc.SCALAR_RTOL, atol=1e-6)
 
 
+def test_bracket_vs_oracle_1080p(gpu_ctx):
+    """Config C2 geometry (the benchmarked size): centres (margin-guarded), cut flags, scalars."""
+    clip = ClipGenerator(ClipSpec(1920, 1080, 18000, seed=0, amplitude=0.15, period=30.0)).stack(7, 14)
+    vals, cuts, infos = mo.process_bracket(list(clip), {})
+    r = api.process_bracket(clip, {}, ctx=gpu_ctx, batch_frames=4, return_flows=True)
+    assert r["n_pairs"] == 6 and np.array_equal(r["cut"], cuts)
+    exact = 0
+    for j, info in enumerate(infos):
+        print(pc.assert_flow_close(r["flows"][j - r["flow_first"]], info["flow"], f"1080p pair {j}"))
+        exact += pc.assert_argmax((r["cx"][j], r["cy"][j]), r["val"][j], info["flow"], f"pair {j}") >= pc.ARGMAX_MARGIN
+        ref = mo.radial_motion_weighted(info["flow"], r["centers"][j], info["cut"])
+        assert abs(r["scalar"][j] - ref) <= pc.SCALAR_RTOL * abs(ref) + pc.scalar_tol(info["flow"], r["centers"][j])
+    assert exact >= 3
+    same = np.all(np.stack([r["cx"], r["cy"]], 1) == np.array([i["pos_center"] for i in infos]), axis=1)
+    if same.all():
+        assert np.allclose(r["scalar"], vals, rtol=pc.SCALAR_RTOL, atol=1e-6)
+
+
 def test_scene_cuts_and_pan(gpu_ctx):
     """Config C3 style (pan + hard cuts) at a CPU-checkable size: identical scene-cut indices."""
     spec = ClipSpec(960, 540, 40, seed=3, amplitude=0.15, period=20.0, pan=(1.5, 0.0), cuts=(13, 29))
