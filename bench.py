@@ -37,13 +37,13 @@ ITER_BYTES_PER_PX = 56.0
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
-    ap.add_argument("--pairs-per-step", type=int, default=64)
-    ap.add_argument("--batch-frames", type=int, default=32)
+    ap.add_argument("--pairs-per-step", type=int, default=128)
+    ap.add_argument("--batch-frames", type=int, default=64)
     ap.add_argument("--cpu-sample-pairs", type=int, default=0, help="0 = 2 x host cores (bounded to 8..64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
