@@ -15,7 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_LIB = os.path.join(_HERE, "libffb.so")
 
-K_NAMES = ["pyramid", "polyexp", "upsample", "flow_iter", "divmag", "radial", "small"]
+K_NAMES = ["pyramid", "polyexp", "upsample", "flow_iter", "divmag", "radial", "small", "preprocess"]
 K_FLOW_ITER = 3
 
 
@@ -64,6 +64,9 @@ def load(path: Optional[str] = None) -> C.CDLL:
         "ffb_stage_update_matrices": (i32, [vp, f32p, f32p, f32p, i32, i32, f32p]),
         "ffb_stage_flow_iter": (i32, [vp, f32p, f32p, f32p, i32, i32, f32p]),
         "ffb_stage_upsample_flow": (i32, [vp, f32p, i32, i32, i32, i32, f32p]),
+        "ffb_preprocess_configure": (i32, [vp, i32, i32, i32]),
+        "ffb_bracket_push_bgr": (i32, [vp, vp, i32, sz, sz]),
+        "ffb_stage_preprocess": (i32, [vp, u8p, i32, i32, sz, i32, u8p]),
         "ffb_profile": (i32, [vp, i32]),
         "ffb_profile_reset": (i32, [vp]),
         "ffb_kernel_stats": (i32, [vp, i32, C.POINTER(C.c_int64), f64p, f64p]),
@@ -191,6 +194,27 @@ class FlowContext:
     def bracket_push_ptr(self, ptr: int, n: int, pitch: int, frame_stride: int):
         """Raw pointer variant (device pointers, e.g. torch_tensor.data_ptr())."""
         self._ck(self._lib.ffb_bracket_push(self._h, C.c_void_p(ptr), int(n), int(pitch), int(frame_stride)))
+
+    def preprocess_configure(self, src_width: int, src_height: int, vr_mode: bool = False):
+        """Source geometry of decoded BGR frames for bracket_push_bgr (output is always 256x256)."""
+        self._ck(self._lib.ffb_preprocess_configure(self._h, int(src_width), int(src_height), int(bool(vr_mode))))
+
+    def bracket_push_bgr(self, frames: np.ndarray):
+        """frames: uint8 [n, H, W, 3] (or [H, W, 3]) BGR as decoded; resized + gray-converted on the GPU."""
+        if frames.ndim == 3:
+            frames = frames[None]
+        assert frames.dtype == np.uint8 and frames.ndim == 4 and frames.shape[3] == 3
+        assert frames.strides[3] == 1 and frames.strides[2] == 3
+        n = frames.shape[0]
+        stride = frames.strides[0] if n > 1 else frames.strides[1] * frames.shape[1]
+        self._ck(self._lib.ffb_bracket_push_bgr(self._h, frames.ctypes.data, n, frames.strides[1], stride))
+
+    def stage_preprocess(self, bgr: np.ndarray, vr_mode: bool = False) -> np.ndarray:
+        bgr = np.ascontiguousarray(bgr, dtype=np.uint8)
+        h, w = bgr.shape[:2]
+        out = np.empty((256, 256), np.uint8)
+        self._ck(self._lib.ffb_stage_preprocess(self._h, _u8(bgr), w, h, w * 3, int(bool(vr_mode)), _u8(out)))
+        return out
 
     def bracket_finish(self):
         m = self.geometry[3]

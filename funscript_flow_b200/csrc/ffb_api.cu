@@ -25,7 +25,7 @@ namespace {
 thread_local std::string g_create_error;
 
 const char* const kKernelNames[FFB_K_COUNT] = {"k_pyramid_level", "k_polyexp",  "k_upsample_flow", "k_flow_iter",
-                                               "k_divmag",        "k_radial",   "small"};
+                                               "k_divmag",        "k_radial",   "small",           "k_preprocess"};
 
 // ------------------------------------------------------------------ host-side constant builders
 int cv_round(double v) { return (int)nearbyint(v); }   // round-half-even in the default FP mode
@@ -203,6 +203,13 @@ struct ffb_ctx {
     double *d_psum = nullptr, *d_rpart = nullptr;
     int div_nblk = 0, div_rpb = 0, div_gx = 0, div_gy = 0, rad_gx = 0, rad_gy = 0, rad_rpb = 0;
     char* h_res = nullptr;    // pinned result staging
+    // frame pre-processing (row N2): source geometry, tables, chunked colour staging
+    int pre_W = 0, pre_H = 0, pre_vr = 0, pre_T = 0;      // pre_T = resize target (256 or 512)
+    int *pre_xt = nullptr, *pre_yt = nullptr;
+    uint8_t* d_color[2] = {nullptr, nullptr};
+    uint8_t* h_color[2] = {nullptr, nullptr};
+    cudaEvent_t ev_ch2d[2] = {nullptr, nullptr}, ev_pre[2] = {nullptr, nullptr};
+    int color_no = 0;
     // bracket state
     bool in_bracket = false;
     int pov = 0;
@@ -815,6 +822,59 @@ struct Scratch {   // frees everything it allocated when the hook returns
 };
 }  // namespace
 
+// ------------------------------------------------------------------ frame pre-processing (row N2)
+constexpr int PRE_CHUNK = 8;      // colour frames per staging chunk
+constexpr int PRE_OUT = 256;
+
+// cv::resize INTER_LINEAR uint8 tables: [x0 | x1 | a0 | a1] (x: weights reset where the footprint
+// leaves the image; y: only the indices are clipped) -- see oracle/preproc_np.py.
+std::vector<int> make_u8_resize_table(int dst_n, int src_n, bool reset_at_borders) {
+    std::vector<int> t(4 * (size_t)dst_n);
+    const double scale = (double)src_n / dst_n;
+    for (int d = 0; d < dst_n; ++d) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s0 = (int)floorf(f);
+        f -= (float)s0;
+        if (reset_at_borders) {
+            if (s0 < 0) { s0 = 0; f = 0.f; }
+            if (s0 >= src_n - 1) { s0 = src_n - 1; f = 0.f; }
+        }
+        const int a1 = (int)nearbyintf(f * 2048.f);
+        const int a0 = (int)nearbyintf((1.f - f) * 2048.f);
+        auto clip = [&](int v) { return v < 0 ? 0 : (v > src_n - 1 ? src_n - 1 : v); };
+        t[d] = clip(s0);
+        t[dst_n + d] = clip(s0 + 1);
+        t[2 * dst_n + d] = a0;
+        t[3 * dst_n + d] = a1;
+    }
+    return t;
+}
+
+void free_preprocess(ffb_ctx* c) {
+    dev_free(c->pre_xt); dev_free(c->pre_yt);
+    for (int b = 0; b < 2; ++b) {
+        dev_free(c->d_color[b]);
+        if (c->h_color[b]) cudaFreeHost(c->h_color[b]);
+        c->h_color[b] = nullptr;
+    }
+    c->pre_W = c->pre_H = 0;
+}
+
+int launch_preprocess(ffb_ctx* c, const uint8_t* src, size_t stride, int pitch, uint8_t* dst, size_t dstride, int dpitch,
+                      const int* xt, const int* yt, int T, int vr, int W, int H, int n) {
+    FfbPreArgs a;
+    a.src = src; a.src_frame_stride = stride; a.src_pitch = pitch;
+    a.dst = dst; a.dst_frame_stride = dstride; a.dst_pitch = dpitch;
+    a.xt = xt; a.yt = yt; a.TW = T; a.TH = T; a.y_off = vr ? T / 2 : 0;
+    // algorithmic bytes: the 2x2 footprint of every output pixel (3 bytes each) + the gray output
+    prof_begin(c, FFB_K_PREPROC, (double)n * (PRE_OUT * PRE_OUT * 13.0));
+    FFB_LAUNCH(k_preprocess, dim3(PRE_OUT / 32, PRE_OUT / 8, n), dim3(256), 0, c->s_comp, a);
+    prof_end(c);
+    CKL(c);
+    (void)W; (void)H;
+    return FFB_OK;
+}
+
 // ======================================================================================
 // extern "C" ABI
 // ======================================================================================
@@ -856,6 +916,10 @@ int ffb_create(int device, ffb_ctx** out) {
         cudaEventCreateWithFlags(&c->ev_expand[b], cudaEventDisableTiming);
         cudaEventRecord(c->ev_h2d[b], c->s_copy);
         cudaEventRecord(c->ev_expand[b], c->s_comp);
+        cudaEventCreateWithFlags(&c->ev_ch2d[b], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&c->ev_pre[b], cudaEventDisableTiming);
+        cudaEventRecord(c->ev_ch2d[b], c->s_copy);
+        cudaEventRecord(c->ev_pre[b], c->s_comp);
     }
     c->poly = make_poly_consts();
     *out = c;
@@ -871,7 +935,11 @@ void ffb_destroy(ffb_ctx* c) {
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : c->timers) if (e) cudaEventDestroy(e);
     free_geometry(c);
-    for (int b = 0; b < 2; ++b) { cudaEventDestroy(c->ev_h2d[b]); cudaEventDestroy(c->ev_expand[b]); }
+    free_preprocess(c);
+    for (int b = 0; b < 2; ++b) {
+        cudaEventDestroy(c->ev_h2d[b]); cudaEventDestroy(c->ev_expand[b]);
+        cudaEventDestroy(c->ev_ch2d[b]); cudaEventDestroy(c->ev_pre[b]);
+    }
     cudaStreamDestroy(c->s_comp);
     cudaStreamDestroy(c->s_copy);
     delete c;
@@ -1218,6 +1286,109 @@ int ffb_stage_upsample_flow(ffb_ctx* c, const float* flow_c, int wc, int hc, int
     TRY(launch_upsample(c, dsrc, 0, wc, wc, hc, ddst, 0, w, w, h, dxi, dxa, dyi, dya, 1));
     CK(c, cudaStreamSynchronize(c->s_comp));
     CK(c, cudaMemcpy(out, ddst, (size_t)w * h * 8, cudaMemcpyDeviceToHost));
+    return FFB_OK;
+}
+
+// ---- frame pre-processing (row N2) --------------------------------------------------------
+int ffb_preprocess_configure(ffb_ctx* c, int W, int H, int vr) {
+    if (!c || W < 2 || H < 2) return fail(c, FFB_E_INVALID, "ffb_preprocess_configure: bad geometry");
+    CK(c, cudaSetDevice(c->device));
+    if (c->in_bracket) return fail(c, FFB_E_INVALID, "ffb_preprocess_configure inside a bracket");
+    if (c->pre_W == W && c->pre_H == H && c->pre_vr == (vr ? 1 : 0)) return FFB_OK;
+    CK(c, cudaStreamSynchronize(c->s_comp));
+    CK(c, cudaStreamSynchronize(c->s_copy));
+    free_preprocess(c);
+    const int T = vr ? 2 * PRE_OUT : PRE_OUT;
+    TRY(upload_vec(c, &c->pre_xt, make_u8_resize_table(T, W, true)));
+    TRY(upload_vec(c, &c->pre_yt, make_u8_resize_table(T, H, false)));
+    const size_t cbytes = (size_t)PRE_CHUNK * W * H * 3;
+    for (int b = 0; b < 2; ++b) {
+        TRY(dev_alloc(c, &c->d_color[b], cbytes));
+        void* hp = nullptr;
+        if (cudaHostAlloc(&hp, cbytes, cudaHostAllocDefault) != cudaSuccess)
+            return fail(c, FFB_E_NOMEM, "cudaHostAlloc(%zu) failed", cbytes);
+        c->h_color[b] = (uint8_t*)hp;
+    }
+    c->pre_W = W; c->pre_H = H; c->pre_vr = vr ? 1 : 0; c->pre_T = T;
+    return FFB_OK;
+}
+
+int ffb_bracket_push_bgr(ffb_ctx* c, const uint8_t* bgr, int n, size_t pitch, size_t stride) {
+    if (!c || !c->in_bracket) return fail(c, FFB_E_INVALID, "ffb_bracket_push_bgr outside a bracket");
+    if (c->pre_W == 0) return fail(c, FFB_E_INVALID, "ffb_bracket_push_bgr before ffb_preprocess_configure");
+    if (c->W != PRE_OUT || c->H != PRE_OUT) return fail(c, FFB_E_INVALID, "pre-processed frames are 256x256: ffb_configure(ctx, 256, 256, ...)");
+    const size_t row = (size_t)c->pre_W * 3;
+    if (!bgr || n < 0 || pitch < row || stride < pitch * (size_t)(c->pre_H - 1) + row)
+        return fail(c, FFB_E_INVALID, "ffb_bracket_push_bgr: bad arguments");
+    const PtrKind kind = classify(bgr);
+    const size_t fbytes = row * c->pre_H;
+    for (int i = 0; i < n;) {
+        int cap = c->frames_seen == 0 ? c->B + 1 : c->B;
+        if (c->frames_seen == 0 && kind != PTR_DEVICE && c->B >= 8) cap = c->B / 4 + 1;
+        const int nb = n - i < cap ? n - i : cap;
+        const int b = c->batch_no & 1;
+        for (int j = 0; j < nb; j += PRE_CHUNK) {
+            const int m = nb - j < PRE_CHUNK ? nb - j : PRE_CHUNK;
+            const uint8_t* src = bgr + (size_t)(i + j) * stride;
+            const uint8_t* dsrc = src;
+            size_t dstride = stride;
+            int dpitch = (int)pitch;
+            if (kind != PTR_DEVICE) {
+                const int cb = c->color_no & 1;
+                c->color_no++;
+                CK(c, cudaStreamWaitEvent(c->s_copy, c->ev_pre[cb], 0));      // kernel that last read d_color[cb]
+                if (kind == PTR_PAGEABLE) {
+                    CK(c, cudaEventSynchronize(c->ev_ch2d[cb]));              // DMA that last read h_color[cb]
+                    for (int f = 0; f < m; ++f) {
+                        const uint8_t* s0 = src + (size_t)f * stride;
+                        uint8_t* d0 = c->h_color[cb] + (size_t)f * fbytes;
+                        if (pitch == row) memcpy(d0, s0, fbytes);
+                        else for (int y = 0; y < c->pre_H; ++y) memcpy(d0 + (size_t)y * row, s0 + (size_t)y * pitch, row);
+                    }
+                    CK(c, cudaMemcpyAsync(c->d_color[cb], c->h_color[cb], (size_t)m * fbytes, cudaMemcpyHostToDevice, c->s_copy));
+                } else if (pitch == row && stride == fbytes) {
+                    CK(c, cudaMemcpyAsync(c->d_color[cb], src, (size_t)m * fbytes, cudaMemcpyHostToDevice, c->s_copy));
+                } else {
+                    for (int f = 0; f < m; ++f)
+                        CK(c, cudaMemcpy2DAsync(c->d_color[cb] + (size_t)f * fbytes, row, src + (size_t)f * stride, pitch, row,
+                                                c->pre_H, cudaMemcpyHostToDevice, c->s_copy));
+                }
+                CK(c, cudaEventRecord(c->ev_ch2d[cb], c->s_copy));
+                CK(c, cudaStreamWaitEvent(c->s_comp, c->ev_ch2d[cb], 0));
+                dsrc = c->d_color[cb];
+                dstride = fbytes;
+                dpitch = (int)row;
+                TRY(launch_preprocess(c, dsrc, dstride, dpitch, c->d_u8[b] + (size_t)j * PRE_OUT * PRE_OUT, (size_t)PRE_OUT * PRE_OUT,
+                                      PRE_OUT, c->pre_xt, c->pre_yt, c->pre_T, c->pre_vr, c->pre_W, c->pre_H, m));
+                CK(c, cudaEventRecord(c->ev_pre[cb], c->s_comp));
+            } else {
+                TRY(launch_preprocess(c, dsrc, dstride, dpitch, c->d_u8[b] + (size_t)j * PRE_OUT * PRE_OUT, (size_t)PRE_OUT * PRE_OUT,
+                                      PRE_OUT, c->pre_xt, c->pre_yt, c->pre_T, c->pre_vr, c->pre_W, c->pre_H, m));
+            }
+        }
+        // the gray frames now sit in the device staging buffer: continue as for device input
+        TRY(process_batch(c, c->d_u8[b], nb, PRE_OUT, (size_t)PRE_OUT * PRE_OUT, PTR_DEVICE));
+        i += nb;
+    }
+    return FFB_OK;
+}
+
+int ffb_stage_preprocess(ffb_ctx* c, const uint8_t* bgr, int W, int H, size_t pitch, int vr, uint8_t* gray) {
+    if (!c || !bgr || !gray || W < 2 || H < 2) return FFB_E_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    const int T = vr ? 2 * PRE_OUT : PRE_OUT;
+    Scratch s;
+    uint8_t *d_src, *d_dst;
+    int *dxt, *dyt;
+    const std::vector<int> xt = make_u8_resize_table(T, W, true), yt = make_u8_resize_table(T, H, false);
+    TRY(s.alloc(c, &d_src, (size_t)W * H * 3));
+    CK(c, cudaMemcpy2D(d_src, (size_t)W * 3, bgr, pitch, (size_t)W * 3, H, cudaMemcpyHostToDevice));
+    TRY(s.alloc(c, &d_dst, (size_t)PRE_OUT * PRE_OUT));
+    TRY(s.upload(c, &dxt, xt.data(), xt.size()));
+    TRY(s.upload(c, &dyt, yt.data(), yt.size()));
+    TRY(launch_preprocess(c, d_src, (size_t)W * H * 3, W * 3, d_dst, (size_t)PRE_OUT * PRE_OUT, PRE_OUT, dxt, dyt, T, vr, W, H, 1));
+    CK(c, cudaStreamSynchronize(c->s_comp));
+    CK(c, cudaMemcpy(gray, d_dst, (size_t)PRE_OUT * PRE_OUT, cudaMemcpyDeviceToHost));
     return FFB_OK;
 }
 

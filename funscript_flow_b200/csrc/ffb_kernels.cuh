@@ -957,3 +957,41 @@ __global__ void __launch_bounds__(32) k_radial_finish(const double* partial, int
     s = ffb_warp_sum(s);
     if (threadIdx.x == 0) scalar[out0 + pair] = s / ((double)w * (double)h);
 }
+
+// ======================================================================================
+// N2  frame pre-processing: decoded BGR frame -> 256 x 256 gray  (F:173-189, F:1057-1082)
+// ======================================================================================
+// cv2.resize(INTER_LINEAR) in OpenCV's 8-bit fixed-point arithmetic (11-bit weights, horizontal pass
+// in int, vertical  (((b0*(H0>>4))>>16) + ((b1*(H1>>4))>>16) + 2) >> 2 ) on the RGB channels, then
+// cv2.cvtColor(RGB2GRAY) = (9798 R + 19235 G + 3735 B + 16384) >> 15.  Integer work: bit-exact.
+// VR mode: the resize target is 512 x 512 and only its bottom-left 256 x 256 quadrant is produced.
+struct FfbPreArgs {
+    const uint8_t* src; size_t src_frame_stride; int src_pitch;   // BGR, 3 bytes per pixel
+    uint8_t* dst; size_t dst_frame_stride; int dst_pitch;          // gray 256 x 256
+    const int* xt;    // [4][TW]: x0, x1, a0, a1 per resized column
+    const int* yt;    // [4][TH]: y0, y1, b0, b1 per resized row
+    int TW, TH;       // resize target (256 x 256, or 512 x 512 in VR mode)
+    int y_off;        // first resized row that is kept (0, or 256 in VR mode)
+};
+
+__global__ void __launch_bounds__(256) k_preprocess(FfbPreArgs a) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= 256 || y >= 256) return;
+    const int ry = y + a.y_off;
+    const int x0 = a.xt[x] * 3, x1 = a.xt[a.TW + x] * 3, a0 = a.xt[2 * a.TW + x], a1 = a.xt[3 * a.TW + x];
+    const int y0 = a.yt[ry], y1 = a.yt[a.TH + ry], b0 = a.yt[2 * a.TH + ry], b1 = a.yt[3 * a.TH + ry];
+    const uint8_t* src = a.src + (size_t)blockIdx.z * a.src_frame_stride;
+    const uint8_t* r0 = src + (size_t)y0 * a.src_pitch;
+    const uint8_t* r1 = src + (size_t)y1 * a.src_pitch;
+    int rgb[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {          // ch indexes RGB; the source is BGR
+        const int o = 2 - ch;
+        const int h0 = (int)__ldg(r0 + x0 + o) * a0 + (int)__ldg(r0 + x1 + o) * a1;
+        const int h1 = (int)__ldg(r1 + x0 + o) * a0 + (int)__ldg(r1 + x1 + o) * a1;
+        rgb[ch] = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+    }
+    const int gray = (9798 * rgb[0] + 19235 * rgb[1] + 3735 * rgb[2] + 16384) >> 15;
+    a.dst[(size_t)blockIdx.z * a.dst_frame_stride + (size_t)y * a.dst_pitch + x] = (uint8_t)gray;
+}

@@ -11,8 +11,9 @@ bracket ends: F:1145-1153, 1188, 1203-1214); `step = ceil(fps/30)` sub-sampling 
 the .funscript exists unless `overwrite` (F:1105-1109).  The reference's prefetch race (SURVEY
 section 5.3) is *not* reproduced: every bracket is computed on its own frames.
 
-Frame acquisition (decode, resize to 256x256 or the VR crop, RGB->gray: F:1051-1091) stays on the
-host with cv2 -- it is outside the hot path; the hot path starts at the grayscale frames.
+Frame acquisition: decode stays on the host (cv2.VideoCapture); the resize to 256x256 (or the VR crop)
+and RGB->gray of F:1051-1091 run on the GPU (`ffb_bracket_push_bgr`, bit-exact with cv2's
+8-bit fixed-point arithmetic), so the decoded BGR frames are the only thing that crosses PCIe.
 """
 from __future__ import annotations
 
@@ -60,39 +61,110 @@ def process_frames(frames: Sequence[np.ndarray], fps: float, params: Dict, frame
     return actions
 
 
-def read_sampled_gray(video_path: str, indices: Sequence[int], params: Dict) -> List[np.ndarray]:
-    """Frames `indices` of the video as the reference feeds them to the flow (F:1051-1091):
-    BGR->RGB, resize to 256x256 (VR: 512x512 then the bottom-left 256x256), RGB->gray."""
+def iter_sampled_bgr(video_path: str, indices: Sequence[int]):
+    """Decode the sampled frames (BGR, as cv2.VideoCapture returns them); undecodable frames are black
+    (F:274-280).  Sequential read + grab instead of the reference's per-frame seek."""
     import cv2
     cap = cv2.VideoCapture(video_path)
     if not cap.isOpened():
         raise IOError(f"cannot open {video_path}")
     want = set(int(i) for i in indices)
     last = max(want) if want else -1
-    out = []
+    shape = None
     pos = 0
-    vr = bool(params.get("vr_mode"))
     while pos <= last:
         if pos in want:
             ok, frame = cap.read()
-            if not ok:      # F:274-280: undecodable frames become black
-                frame = np.zeros((256, 256, 3), np.uint8)
-            rgb = cv2.cvtColor(frame, cv2.COLOR_BGR2RGB)
-            if vr:
-                rgb = cv2.resize(rgb, (512, 512))[256:, :256]
+            if ok:
+                shape = frame.shape
             else:
-                rgb = cv2.resize(rgb, (256, 256))
-            out.append(cv2.cvtColor(rgb, cv2.COLOR_RGB2GRAY))
+                frame = np.zeros(shape or (256, 256, 3), np.uint8)
+            yield frame
         else:
             cap.grab()
         pos += 1
     cap.release()
+
+
+def read_sampled_gray(video_path: str, indices: Sequence[int], params: Dict) -> List[np.ndarray]:
+    """HOST version of the frame contract (F:1051-1091), kept for tests: BGR->RGB, resize to 256x256
+    (VR: 512x512 then the bottom-left 256x256), RGB->gray with cv2.  process_video() does the same
+    arithmetic on the GPU (ffb_bracket_push_bgr, bit-exact)."""
+    import cv2
+    out = []
+    vr = bool(params.get("vr_mode"))
+    for frame in iter_sampled_bgr(video_path, indices):
+        rgb = cv2.cvtColor(frame, cv2.COLOR_BGR2RGB)
+        rgb = cv2.resize(rgb, (512, 512))[256:, :256] if vr else cv2.resize(rgb, (256, 256))
+        out.append(cv2.cvtColor(rgb, cv2.COLOR_RGB2GRAY))
     return out
+
+
+def process_video_series(video_path: str, params: Dict, ctx=None, progress_callback=None, cancel_flag=None,
+                         chunk_frames: int = 64):
+    """Bracket loop over a video file with decode on the host and everything else on the GPU:
+    decoded BGR frames are uploaded in chunks, resized + gray-converted (row N2), and run through the
+    hot path.  Returns (values, cuts, frame_indices, fps) or None when cancelled."""
+    import cv2
+    ctx = ctx or api.get_context()
+    cap = cv2.VideoCapture(video_path)
+    if not cap.isOpened():
+        raise IOError(f"cannot open {video_path}")
+    total = int(cap.get(cv2.CAP_PROP_FRAME_COUNT))
+    fps = float(cap.get(cv2.CAP_PROP_FPS))
+    src_w, src_h = int(cap.get(cv2.CAP_PROP_FRAME_WIDTH)), int(cap.get(cv2.CAP_PROP_FRAME_HEIGHT))
+    cap.release()
+    if total < 2 or fps <= 0 or src_w < 2 or src_h < 2:
+        raise IOError("unable to read video properties")
+    ctx.preprocess_configure(src_w, src_h, bool(params.get("vr_mode")))
+    step = postproc.sampling_step(fps)
+    indices = list(range(0, total, step))
+    bracket = int(params.get("batch_size", 3000.0))
+    batch = int(params.get("gpu_batch_frames", 64))
+    values: List[float] = []
+    cuts: List[bool] = []
+    stamps: List[int] = []
+    frames = iter_sampled_bgr(video_path, indices)
+    done = 0
+    for a in range(0, len(indices), bracket):
+        b = min(a + bracket, len(indices))
+        nfr = b - a
+        if cancel_flag and cancel_flag():
+            return None
+        if nfr < 2:          # F:1152-1153 (the frame is still consumed from the decoder)
+            for _ in range(nfr):
+                next(frames, None)
+            continue
+        ctx.configure(256, 256, max(1, min(batch, nfr)), nfr - 1)
+        ctx.bracket_begin(bool(params.get("pov_mode", False)), float(params.get("cut_threshold", api.DEFAULT_CUT_THRESHOLD)))
+        got = 0
+        while got < nfr:
+            chunk = []
+            while len(chunk) < chunk_frames and got + len(chunk) < nfr:
+                f = next(frames, None)
+                if f is None:
+                    break
+                chunk.append(f)
+            if not chunk:
+                break
+            arr = np.ascontiguousarray(np.stack(chunk))
+            if arr.shape[1:3] != (src_h, src_w):
+                ctx.bracket_finish()
+                raise IOError(f"decoded frame size {arr.shape[2]}x{arr.shape[1]} differs from the container's {src_w}x{src_h}")
+            ctx.bracket_push_bgr(arr)   # pageable input is copied into pinned staging before the call returns
+            got += len(chunk)
+            done += len(chunk)
+            if progress_callback:
+                progress_callback(min(100, int(100 * done / len(indices))))
+        r = ctx.bracket_finish()
+        values.extend(r["scalar"].tolist())
+        cuts.extend(r["cut"].tolist())
+        stamps.extend(indices[a:a + r["n_pairs"]])
+    return values, cuts, stamps, fps
 
 
 def process_video(video_path, params, log_func, progress_callback=None, cancel_flag=None, preview_callback=None):
     """Same contract as F:1094: writes <video>.funscript, returns error_occurred."""
-    import cv2
     start = time.time()
     base, _ = os.path.splitext(video_path)
     output_path = base + ".funscript"
@@ -100,30 +172,19 @@ def process_video(video_path, params, log_func, progress_callback=None, cancel_f
         log_func(f"Skipping: output file exists ({output_path})")
         return False
     log_func(f"Processing video: {video_path}")
-    cap = cv2.VideoCapture(video_path)
-    if not cap.isOpened():
-        log_func(f"ERROR: Unable to open video at {video_path}")
-        return True
-    total = int(cap.get(cv2.CAP_PROP_FRAME_COUNT))
-    fps = float(cap.get(cv2.CAP_PROP_FPS))
-    cap.release()
-    if total < 2 or fps <= 0:
-        log_func("ERROR: Unable to read video properties")
-        return True
-    step = postproc.sampling_step(fps)
-    indices = list(range(0, total, step))
-    log_func(f"FPS: {fps:.2f}; downsampled to ~{fps / step:.2f} fps; {len(indices)} frames selected.")
     log_func("Using backend: B200 (sm_100a)")
     try:
-        frames = read_sampled_gray(video_path, indices, params)
-        actions = process_frames(frames, fps, params, indices[:len(frames)], progress_callback=progress_callback,
-                                 cancel_flag=cancel_flag)
+        res = process_video_series(video_path, params, progress_callback=progress_callback, cancel_flag=cancel_flag)
     except Exception as exc:   # surfaced, never swallowed into a CPU fallback
         log_func(f"ERROR: {exc}")
         return True
-    if actions is None:
+    if res is None:
         log_func("User bailed.")
         return False
+    values, cuts, stamps, fps = res
+    step = postproc.sampling_step(fps)
+    log_func(f"FPS: {fps:.2f}; downsampled to ~{fps / step:.2f} fps; {len(stamps) + 1} frames selected.")
+    actions = postproc.scalars_to_actions(values, cuts, stamps, fps, params) if values else []
     log_func(f"Keyframe reduction: {len(actions)} actions computed.")
     try:
         postproc.write_funscript(output_path, actions)

@@ -123,6 +123,18 @@ int  ffb_stage_flow_iter(ffb_ctx* ctx, const float* R0, const float* R1, const f
 /* A1e: coarse flow [hc][wc][2] -> [h][w][2], bilinear, x2. */
 int  ffb_stage_upsample_flow(ffb_ctx* ctx, const float* flow_c, int wc, int hc, int w, int h, float* out);
 
+/* ---- frame pre-processing on the device (replaces F:173-189 + F:1074-1082) ------
+ * Decoded BGR frames (3 bytes per pixel, as cv2.VideoCapture returns them) are resized to 256 x 256
+ * with cv2.resize's 8-bit fixed-point INTER_LINEAR arithmetic (VR mode: 512 x 512, bottom-left
+ * quadrant) and converted with cv2's RGB2GRAY formula -- bit-exact with the reference's host path.
+ * ffb_preprocess_configure sets the source geometry; the context must be configured for 256 x 256
+ * frames (ffb_configure(ctx, 256, 256, ...)) before ffb_bracket_push_bgr is used. */
+int  ffb_preprocess_configure(ffb_ctx* ctx, int src_width, int src_height, int vr_mode);
+int  ffb_bracket_push_bgr(ffb_ctx* ctx, const uint8_t* bgr, int n_frames, size_t pitch, size_t frame_stride);
+/* Stage hook: one BGR frame -> gray[256][256] on the host. */
+int  ffb_stage_preprocess(ffb_ctx* ctx, const uint8_t* bgr, int width, int height, size_t pitch, int vr_mode,
+                          uint8_t* gray_256x256);
+
 /* ---- instrumentation ----------------------------------------------------------------------
  * Kernel ids for ffb_kernel_stats. */
 #define FFB_K_PYRAMID   0
@@ -132,7 +144,8 @@ int  ffb_stage_upsample_flow(ffb_ctx* ctx, const float* flow_c, int wc, int hc, 
 #define FFB_K_DIVMAG    4
 #define FFB_K_RADIAL    5
 #define FFB_K_SMALL     6   /* finish / centre-smoothing kernels */
-#define FFB_K_COUNT     7
+#define FFB_K_PREPROC   7
+#define FFB_K_COUNT     8
 /* When enabled, every launch of the kernels above is bracketed by CUDA events on the compute
  * stream; ffb_kernel_stats returns launches, summed device milliseconds and the algorithmic
  * bytes those launches moved (DESIGN.md section "bytes per unit") since the last reset. */

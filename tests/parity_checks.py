@@ -234,3 +234,33 @@ def check_postproc_golden(golden_dir):
         assert got == case["actions"]
         ffl = list(zip(case["values"], case["cuts"], case["frame_indices"]))
         assert mo.postprocess(ffl, case["fps"], case["params"]) == case["actions"]
+
+
+def check_preprocess(ctx, sizes=((360, 640), (300, 200), (256, 256))):
+    """Row N2: BGR frame -> 256x256 gray on the device, bit-exact with the oracle (and so with cv2)."""
+    from oracle import preproc_np as pp
+    rng = np.random.default_rng(3)
+    for (h, w) in sizes:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        for vr in (False, True):
+            assert np.array_equal(ctx.stage_preprocess(img, vr), pp.frame_to_gray(img, vr)), (h, w, vr)
+
+
+def check_bgr_push_equals_gray_push(ctx, width=320, height=200, n=7):
+    """The fused upload path (colour frames -> device pre-processing -> hot path) gives exactly the
+    result of pre-processing on the host and pushing gray frames."""
+    import cv2
+    from oracle import preproc_np as pp
+    clip = make_clip(width, height, n, seed=4)
+    bgr = np.stack([cv2.cvtColor(f, cv2.COLOR_GRAY2BGR) for f in clip])
+    bgr[..., 0] = (bgr[..., 0].astype(int) * 3 // 4).astype(np.uint8)      # make the channels differ
+    gray = np.stack([pp.frame_to_gray(f) for f in bgr])
+    ra = api.process_bracket(gray, {}, ctx=ctx, batch_frames=3)
+    ctx.configure(256, 256, 3, n - 1)
+    ctx.preprocess_configure(width, height, False)
+    ctx.bracket_begin(False, 7.0)
+    ctx.bracket_push_bgr(bgr[:4])
+    ctx.bracket_push_bgr(bgr[4:])
+    rb = ctx.bracket_finish()
+    for k in ("scalar", "cut", "cx", "cy", "val", "mean_mag"):
+        assert np.array_equal(ra[k], rb[k]), k

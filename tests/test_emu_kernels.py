@@ -51,3 +51,34 @@ def test_process_frames_brackets(emu_ctx):
     assert len(acts) == 8
     one = api.process_bracket(clip[5:10], {}, ctx=emu_ctx)
     assert np.array_equal(series["values"][4:], one["scalar"])
+
+
+def test_preprocess(emu_ctx):
+    pc.check_preprocess(emu_ctx)
+    pc.check_bgr_push_equals_gray_push(emu_ctx)
+
+
+def test_process_video_file(emu_ctx, tmp_path):
+    """process_video() on a small lossless clip: decode on the host, resize / gray / flow / reductions in
+    the kernels; equals the host pre-processing path and honours the skip-if-exists rule (F:1105-1109)."""
+    import json
+    import cv2
+    api.set_context(emu_ctx)
+    clip = make_clip(160, 120, 9, seed=6, period=7.0, amplitude=0.3)
+    path = str(tmp_path / "tiny.avi")
+    vw = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"FFV1"), 30.0, (160, 120), True)
+    if not vw.isOpened():
+        pytest.skip("FFV1 writer unavailable")
+    for f in clip:
+        vw.write(cv2.cvtColor(f, cv2.COLOR_GRAY2BGR))
+    vw.release()
+    prm = {"batch_size": 3000, "detrend_window": 2.0, "norm_window": 3.0, "keyframe_reduction": False, "overwrite": True,
+           "vr_mode": False, "pov_mode": False, "gpu_batch_frames": 4}
+    logs = []
+    assert runner.process_video(path, prm, logs.append) is False, logs
+    acts = json.load(open(str(tmp_path / "tiny.funscript")))["actions"]
+    gray = runner.read_sampled_gray(path, list(range(9)), prm)
+    ref = runner.process_frames(gray, 30.0, prm, ctx=emu_ctx)
+    assert acts == ref and len(acts) == 8
+    logs.clear()
+    assert runner.process_video(path, dict(prm, overwrite=False), logs.append) is False and any("Skipping" in l for l in logs)

@@ -131,6 +131,13 @@ def test_dropin_functions(gpu_ctx):
     assert api.get_available_backends()["CUDA"] is True
 
 
+def test_preprocess_bit_exact(gpu_ctx):
+    """Row N2: device resize + gray conversion, bit-exact with cv2 (via the oracle), incl. 4K and VR sources."""
+    pc.check_preprocess(gpu_ctx, sizes=((360, 640), (300, 200), (256, 256), (1080, 1920), (2160, 3840), (2880, 5760)))
+    pc.check_bgr_push_equals_gray_push(gpu_ctx)
+    pc.check_bgr_push_equals_gray_push(gpu_ctx, 1920, 1080, 40)
+
+
 def test_process_video_matches_reference_funscript(gpu_ctx, golden_dir, tmp_path):
     """End to end on the C1-style clip: the .funscript written by our process_video() has the same
     keyframe timestamps as the one the reference's process_video() wrote (recorded in video_c1.json)."""

@@ -111,3 +111,18 @@ def test_oracle_vs_live_reference():
     ffl = [(float(vals[i]), i == 77, i) for i in range(200)]
     prm = {"detrend_window": 1.5, "norm_window": 4, "keyframe_reduction": True}
     assert pp(ffl, 30.0, 30.0, prm, lambda *_: None) == mo.postprocess(ffl, 30.0, prm)
+
+
+def test_preprocess_oracle_bit_exact_vs_cv2():
+    """Row N2: cv2.resize (uint8 fixed point) + RGB2GRAY restated; integer work => bit-exact."""
+    from oracle import preproc_np as pp
+    rng = np.random.default_rng(1)
+    for (h, w, dw, dh) in [(360, 640, 512, 512), (256, 256, 512, 512), (300, 200, 512, 512), (200, 300, 256, 256),
+                           (1080, 1920, 256, 256), (97, 131, 256, 256), (480, 854, 256, 256)]:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        assert np.array_equal(cv2.resize(img, (dw, dh)), pp.resize_u8_linear(img, dw, dh)), (h, w, dw, dh)
+    for (h, w) in [(360, 640), (1080, 1920), (256, 256), (300, 200)]:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        rgb = cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
+        assert np.array_equal(cv2.cvtColor(cv2.resize(rgb, (256, 256)), cv2.COLOR_RGB2GRAY), pp.frame_to_gray(img, False))
+        assert np.array_equal(cv2.cvtColor(cv2.resize(rgb, (512, 512))[256:, :256], cv2.COLOR_RGB2GRAY), pp.frame_to_gray(img, True))
