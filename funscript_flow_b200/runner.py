@@ -212,12 +212,30 @@ def shard(items: Sequence, rank: int, world: int) -> List:
     return [it for i, it in enumerate(items) if i % world == rank]
 
 
-def run_headless(input_path: str, settings: Dict, log_func: Callable[[str], None] = print) -> int:
-    """F:2606-2638.  Under torchrun (one process per GPU) each rank takes every world-th video."""
+def run_headless(input_path: str, settings: Dict, log_func: Optional[Callable[[str], None]] = None) -> int:
+    """F:2606-2638: walk the folder, process every supported video, log to run.log and stdout.
+    Under torchrun (one process per GPU) each rank takes every world-th video and writes run.<rank>.log.
+    Returns the number of videos that reported an error."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    logf = None
+    if log_func is None:
+        logf = open("run.log" if world == 1 else f"run.{rank}.log", "w")
+
+        def log_func(msg):
+            logf.write(msg + "\n")
+            logf.flush()
+            print(msg)
     vids = shard(list_videos(input_path), rank, world)
+    if not vids:
+        log_func("No video files found.")
+    else:
+        log_func(f"Found {len(vids)} video file(s)" + (f" for rank {rank}/{world}" if world > 1 else ""))
     errors = 0
-    for v in vids:
-        errors += bool(process_video(v, settings, log_func))
+    for i, v in enumerate(vids):
+        log_func(f"Processing file {i + 1}/{len(vids)}: {v}")
+        errors += bool(process_video(v, settings, log_func, progress_callback=None))
+    log_func("Batch processing complete.")
+    if logf:
+        logf.close()
     return errors

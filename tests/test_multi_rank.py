@@ -61,3 +61,15 @@ def test_video_sharding():
     assert sorted(sum(parts, [])) == sorted(vids) and max(map(len, parts)) - min(map(len, parts)) <= 1
     assert distributed.bracket_ranges(11, 5) == [(0, 5), (5, 10)]
     assert distributed.my_brackets([(0, 5), (5, 10), (10, 15)], 1, 2) == [1]
+
+
+def test_cli_settings_match_reference_quirks():
+    """F:2642-2664: same keys and defaults; the keyframe flag is inverted twice."""
+    from funscript_flow_b200.__main__ import build_parser, settings_from_args
+    s = settings_from_args(build_parser().parse_args(["clip.mp4"]))
+    assert set(s) == {"threads", "detrend_window", "norm_window", "batch_size", "overwrite", "vr_mode", "pov_mode",
+                      "keyframe_reduction", "backend"}
+    assert (s["threads"], s["detrend_window"], s["norm_window"], s["batch_size"]) == (8, 2.0, 3.0, 3000)
+    assert s["keyframe_reduction"] is False and not s["overwrite"] and not s["vr_mode"] and not s["pov_mode"]
+    s = settings_from_args(build_parser().parse_args(["clip.mp4", "--disable_keyframe_reduction", "--vr_mode", "--overwrite"]))
+    assert s["keyframe_reduction"] is True and s["vr_mode"] and s["overwrite"]
