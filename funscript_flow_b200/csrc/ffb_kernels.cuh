@@ -19,13 +19,6 @@
 // ======================================================================================
 // small device helpers
 // ======================================================================================
-__device__ __forceinline__ int ffb_reflect101(int i, int n) {
-    if (n == 1) return 0;
-    const int period = 2 * (n - 1);
-    i %= period;
-    if (i < 0) i += period;
-    return i >= n ? period - i : i;
-}
 __device__ __forceinline__ int ffb_clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 template <class T>

@@ -103,11 +103,9 @@ inline void run_block(unsigned nthreads) {
         makecontext(&f.ctx, (void (*)())fiber_entry, 0);
     }
     for (;;) {
-        bool any_run = false;
         for (unsigned i = 0; i < nthreads; ++i) {
             Fiber& f = g_fibers[i];
             if (f.state != 0) continue;
-            any_run = true;
             g_cur = &f;
             g_threadIdx = f.tid;
             swapcontext(&g_sched, &f.ctx);
@@ -131,10 +129,6 @@ inline void run_block(unsigned nthreads) {
             if (ww && ww == live) {
                 for (unsigned i = lo; i < hi; ++i) if (g_fibers[i].state == 2) g_fibers[i].state = 0;
                 released = true;
-            } else if (ww && wblock + done + ww == nthreads && !any_run) {
-                // part of a warp sits in a shuffle while its other lanes are at __syncthreads
-                fprintf(stderr, "cuda_emu: divergent warp shuffle in block (%u,%u,%u)\n", g_blockIdx.x, g_blockIdx.y, g_blockIdx.z);
-                abort();
             }
         }
         if (!released) {

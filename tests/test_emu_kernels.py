@@ -82,3 +82,35 @@ def test_process_video_file(emu_ctx, tmp_path):
     assert acts == ref and len(acts) == 8
     logs.clear()
     assert runner.process_video(path, dict(prm, overwrite=False), logs.append) is False and any("Skipping" in l for l in logs)
+
+
+def test_headless_folder_sharded_over_ranks(emu_ctx, tmp_path, monkeypatch):
+    """Config C5 in miniature (whole videos sharded over ranks): the union of what ranks 0 and 1 of a
+    2-process job write equals what a single process writes (no collective: videos are independent)."""
+    import json
+    import cv2
+    api.set_context(emu_ctx)
+    monkeypatch.chdir(tmp_path)
+    prm = {"batch_size": 3000, "detrend_window": 2.0, "norm_window": 3.0, "keyframe_reduction": True, "overwrite": True,
+           "vr_mode": False, "pov_mode": False, "gpu_batch_frames": 4}
+    for k in range(3):
+        clip = make_clip(96, 64, 6, seed=20 + k, period=5.0, amplitude=0.3)
+        vw = cv2.VideoWriter(str(tmp_path / f"v{k}.avi"), cv2.VideoWriter_fourcc(*"FFV1"), 30.0, (96, 64), True)
+        if not vw.isOpened():
+            pytest.skip("FFV1 writer unavailable")
+        for f in clip:
+            vw.write(cv2.cvtColor(f, cv2.COLOR_GRAY2BGR))
+        vw.release()
+    monkeypatch.delenv("RANK", raising=False)
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    assert runner.run_headless(str(tmp_path), prm, log_func=lambda m: None) == 0
+    single = {k: json.load(open(str(tmp_path / f"v{k}.funscript"))) for k in range(3)}
+    for k in range(3):
+        (tmp_path / f"v{k}.funscript").unlink()
+    monkeypatch.setenv("WORLD_SIZE", "2")
+    for rank in (0, 1):
+        monkeypatch.setenv("RANK", str(rank))
+        assert runner.run_headless(str(tmp_path), prm, log_func=lambda m: None) == 0
+        present = [k for k in range(3) if (tmp_path / f"v{k}.funscript").exists()]
+        assert present == ([0, 2] if rank == 0 else [0, 1, 2])
+    assert {k: json.load(open(str(tmp_path / f"v{k}.funscript"))) for k in range(3)} == single
