@@ -219,6 +219,7 @@ def main():
     dev_ms = ctx.timer_elapsed_ms(0, 1)
     launches = ctx.launch_count - l0
     stats = ctx.kernel_stats()
+    by_level = ctx.flow_iter_level_stats()
     ctx.profile(False)
     # ---- end-to-end arm ("e2e") -----------------------------------------------------------------
     for _ in range(max(1, args.warmup // 2)):
@@ -267,6 +268,10 @@ def main():
                          "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
                          "alg_bytes_per_launch": it["alg_bytes"] / max(1, it["launches"]),
                          "avg_launch_ms": it["ms"] / max(1, it["launches"]), "launches": it["launches"],
+                         "by_level": {f"k{k}": {"launches": v["launches"], "ms_per_launch": v["ms"] / v["launches"],
+                                                "achieved": v["alg_bytes"] / (v["ms"] / 1000.0) / 1e9 if v["ms"] > 0 else 0.0,
+                                                "frac": (v["alg_bytes"] / (v["ms"] / 1000.0) / 1e9 / peak) if v["ms"] > 0 else 0.0}
+                                      for k, v in sorted(by_level.items())},
                          "whole_path_bytes_per_pair": 269.7 * W * H,
                          "whole_path_frac": 269.7 * W * H * value / world / 1e9 / peak},
             "kernel_ms_per_step": kernel_ms,

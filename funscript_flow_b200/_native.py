@@ -70,6 +70,7 @@ def load(path: Optional[str] = None) -> C.CDLL:
         "ffb_profile": (i32, [vp, i32]),
         "ffb_profile_reset": (i32, [vp]),
         "ffb_kernel_stats": (i32, [vp, i32, C.POINTER(C.c_int64), f64p, f64p]),
+        "ffb_flow_iter_level_stats": (i32, [vp, i32, C.POINTER(C.c_int64), f64p, f64p]),
         "ffb_launch_count": (C.c_int64, [vp]),
         "ffb_kernel_name": (C.c_char_p, [i32]),
         "ffb_timer_mark": (i32, [vp, i32]),
@@ -341,6 +342,16 @@ class FlowContext:
             n, ms, by = C.c_int64(), C.c_double(), C.c_double()
             self._ck(self._lib.ffb_kernel_stats(self._h, kid, C.byref(n), C.byref(ms), C.byref(by)))
             out[name] = dict(launches=int(n.value), ms=float(ms.value), alg_bytes=float(by.value))
+        return out
+
+    def flow_iter_level_stats(self):
+        """k_flow_iter launches / device ms / algorithmic bytes per pyramid level k (0 = full resolution)."""
+        out = {}
+        for k in range(4):
+            n, ms, by = C.c_int64(), C.c_double(), C.c_double()
+            self._ck(self._lib.ffb_flow_iter_level_stats(self._h, k, C.byref(n), C.byref(ms), C.byref(by)))
+            if n.value:
+                out[k] = dict(launches=int(n.value), ms=float(ms.value), alg_bytes=float(by.value))
         return out
 
     def timer_mark(self, slot: int):

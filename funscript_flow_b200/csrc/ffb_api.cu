@@ -174,7 +174,7 @@ struct Level {
     float2 *fA = nullptr, *fB = nullptr;   // [B][h][fp]
 };
 
-struct ProfRec { int kid; double bytes; cudaEvent_t e0, e1; };
+struct ProfRec { int kid; int level; double bytes; cudaEvent_t e0, e1; };
 
 }  // namespace
 
@@ -221,6 +221,9 @@ struct ffb_ctx {
     std::vector<cudaEvent_t> ev_pool;
     int64_t k_launches[FFB_K_COUNT] = {0};
     double k_ms[FFB_K_COUNT] = {0}, k_bytes[FFB_K_COUNT] = {0};
+    int64_t it_launches[FFB_MAX_LEVELS] = {0};          // k_flow_iter split by level k
+    double it_ms[FFB_MAX_LEVELS] = {0}, it_bytes[FFB_MAX_LEVELS] = {0};
+    int cur_level = -1;                                  // level k of the flow iteration being launched
     int64_t launches = 0;
     cudaEvent_t timers[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
@@ -280,9 +283,12 @@ void prof_begin(ffb_ctx* c, int kid, double bytes) {
     c->launches++;
     c->k_launches[kid]++;
     c->k_bytes[kid] += bytes;
+    const int lvl = (kid == FFB_K_FLOW_ITER && c->cur_level >= 0 && c->cur_level < FFB_MAX_LEVELS) ? c->cur_level : -1;
+    if (lvl >= 0) { c->it_launches[lvl]++; c->it_bytes[lvl] += bytes; }
     if (!c->prof) return;
     ProfRec r;
     r.kid = kid;
+    r.level = lvl;
     r.bytes = bytes;
     for (cudaEvent_t* e : {&r.e0, &r.e1}) {
         if (!c->ev_pool.empty()) { *e = c->ev_pool.back(); c->ev_pool.pop_back(); }
@@ -301,6 +307,7 @@ void prof_collect(ffb_ctx* c) {
         cudaEventSynchronize(r.e1);
         cudaEventElapsedTime(&ms, r.e0, r.e1);
         c->k_ms[r.kid] += ms;
+        if (r.level >= 0) c->it_ms[r.level] += ms;
         c->ev_pool.push_back(r.e0);
         c->ev_pool.push_back(r.e1);
     }
@@ -653,6 +660,7 @@ int expand_frames(ffb_ctx* c, const uint8_t* src, size_t stride, int pitch, int 
 int flow_pairs(ffb_ctx* c, int p0, int np) {
     for (int l = 0; l < c->nlev; ++l) {
         Level& L = c->lev[l];
+        c->cur_level = L.k;
         FfbRing R;
         R.base = (char*)(c->R + L.r_off);
         R.stride = c->r_slot_floats * sizeof(float);
@@ -683,6 +691,7 @@ int flow_pairs(ffb_ctx* c, int p0, int np) {
         TRY(launch_flow_iter(c, R, L.plane, L.rp, L.w, L.h, L.fB, fstride, L.fp, toA, L.fp, np));
         TRY(launch_flow_iter(c, R, L.plane, L.rp, L.w, L.h, L.fA, fstride, L.fp, last ? toRing : toB, L.fp, np));
     }
+    c->cur_level = -1;
     return FFB_OK;
 }
 
@@ -1405,6 +1414,7 @@ int ffb_profile_reset(ffb_ctx* c) {
     CK(c, cudaStreamSynchronize(c->s_comp));
     prof_collect(c);
     for (int i = 0; i < FFB_K_COUNT; ++i) { c->k_launches[i] = 0; c->k_ms[i] = 0; c->k_bytes[i] = 0; }
+    for (int i = 0; i < FFB_MAX_LEVELS; ++i) { c->it_launches[i] = 0; c->it_ms[i] = 0; c->it_bytes[i] = 0; }
     return FFB_OK;
 }
 int ffb_kernel_stats(ffb_ctx* c, int kid, int64_t* launches, double* ms, double* bytes) {
@@ -1414,6 +1424,15 @@ int ffb_kernel_stats(ffb_ctx* c, int kid, int64_t* launches, double* ms, double*
     if (launches) *launches = c->k_launches[kid];
     if (ms) *ms = c->k_ms[kid];
     if (bytes) *bytes = c->k_bytes[kid];
+    return FFB_OK;
+}
+int ffb_flow_iter_level_stats(ffb_ctx* c, int k, int64_t* launches, double* ms, double* bytes) {
+    if (!c || k < 0 || k >= FFB_MAX_LEVELS) return FFB_E_INVALID;
+    CK(c, cudaStreamSynchronize(c->s_comp));
+    prof_collect(c);
+    if (launches) *launches = c->it_launches[k];
+    if (ms) *ms = c->it_ms[k];
+    if (bytes) *bytes = c->it_bytes[k];
     return FFB_OK;
 }
 int64_t ffb_launch_count(const ffb_ctx* c) { return c ? c->launches : 0; }

@@ -152,6 +152,8 @@ int  ffb_stage_preprocess(ffb_ctx* ctx, const uint8_t* bgr, int width, int heigh
 int  ffb_profile(ffb_ctx* ctx, int enable);
 int  ffb_profile_reset(ffb_ctx* ctx);
 int  ffb_kernel_stats(ffb_ctx* ctx, int kernel_id, int64_t* launches, double* ms, double* alg_bytes);
+/* The same three figures for k_flow_iter alone, split by pyramid level k (0 = full resolution). */
+int  ffb_flow_iter_level_stats(ffb_ctx* ctx, int level_k, int64_t* launches, double* ms, double* alg_bytes);
 int64_t ffb_launch_count(const ffb_ctx* ctx);   /* kernels launched by this context so far */
 /* Device-side stopwatch on the compute stream (the stream every kernel is launched on):
  * ffb_timer_mark(ctx, slot) records CUDA event `slot` (0..7); ffb_timer_elapsed waits for both
