@@ -460,27 +460,16 @@ int launch_flow_iter(ffb_ctx* c, FfbRing R, size_t plane, int rp, int w, int h, 
     }
     const double bytes = (double)npairs * bpp * w * h;
     const IterCfg k = iter_cfg();
+    // Variants kept after the round-1 sweeps (profiles/r1_sweep*.txt); the third number of FFB_ITER_CFG
+    // selects min blocks per SM, with 6 / 7 meaning "horizontal phase first" (/ 8 outputs per task).
     const int key = k.nt * 100 + k.u * 10 + k.minb;
     switch (key) {
-        case 12823: return launch_flow_iter_t<128, 2, 3>(c, a, npairs, k.sh, bytes);
-        case 12825: return launch_flow_iter_t<128, 2, 5>(c, a, npairs, k.sh, bytes);
-        case 12814: return launch_flow_iter_t<128, 1, 4>(c, a, npairs, k.sh, bytes);
-        case 12815: return launch_flow_iter_t<128, 1, 5>(c, a, npairs, k.sh, bytes);
-        case 12842: return launch_flow_iter_t<128, 4, 2>(c, a, npairs, k.sh, bytes);
-        case 12843: return launch_flow_iter_t<128, 4, 3>(c, a, npairs, k.sh, bytes);
-        case 19222: return launch_flow_iter_t<192, 2, 2>(c, a, npairs, k.sh, bytes);
-        case 25622: return launch_flow_iter_t<256, 2, 2>(c, a, npairs, k.sh, bytes);
-        case 6424:  return launch_flow_iter_t<64, 2, 4>(c, a, npairs, k.sh, bytes);
-        case 6428:  return launch_flow_iter_t<64, 2, 8>(c, a, npairs, k.sh, bytes);
-        case 12826: return launch_flow_iter_t<128, 2, 4, true>(c, a, npairs, k.sh, bytes);   // "x6": horizontal first
-        case 12816: return launch_flow_iter_t<128, 1, 5, true>(c, a, npairs, k.sh, bytes);
-        case 12846: return launch_flow_iter_t<128, 4, 3, true>(c, a, npairs, k.sh, bytes);
-        case 25626: return launch_flow_iter_t<256, 2, 2, true>(c, a, npairs, k.sh, bytes);
-        case 12824: return launch_flow_iter_t<128, 2, 4>(c, a, npairs, k.sh, bytes);
-        case 12827: return launch_flow_iter_t<128, 2, 4, true, 8>(c, a, npairs, k.sh, bytes);   // "x7": hfirst, 8 outputs/task
-        case 12847: return launch_flow_iter_t<128, 4, 3, true, 8>(c, a, npairs, k.sh, bytes);
-        case 25627: return launch_flow_iter_t<256, 2, 2, true, 8>(c, a, npairs, k.sh, bytes);
-        default:    return launch_flow_iter_t<128, 2, 4, true>(c, a, npairs, k.sh, bytes);   // 128x2, horizontal first
+        case 12823: return launch_flow_iter_t<128, 2, 3>(c, a, npairs, k.sh, bytes);             // gather first, 3 CTAs/SM
+        case 12824: return launch_flow_iter_t<128, 2, 4>(c, a, npairs, k.sh, bytes);             // gather first, 4 CTAs/SM
+        case 12827: return launch_flow_iter_t<128, 2, 4, true, 8>(c, a, npairs, k.sh, bytes);    // hfirst, 8 outputs / task
+        case 12846: return launch_flow_iter_t<128, 4, 3, true>(c, a, npairs, k.sh, bytes);       // 4 rows / step
+        case 25626: return launch_flow_iter_t<256, 2, 2, true>(c, a, npairs, k.sh, bytes);       // 256-thread strips
+        default:    return launch_flow_iter_t<128, 2, 4, true>(c, a, npairs, k.sh, bytes);       // 128x2, horizontal first
     }
 }
 

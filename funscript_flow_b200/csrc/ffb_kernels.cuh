@@ -922,10 +922,11 @@ __global__ void __launch_bounds__(256) k_radial(FfbRadArgs a) {
         const double wxd = a.pov ? 1.0 : (((double)x > cx) ? (double)(w - x) / (double)w : (double)x / (double)w);
         const float wx = (float)wxd;
         const float ax = (float)(wxd * ((double)x - cx));
+        const double inv_h = 1.0 / (double)h;      // one division per thread, not one per row
 #pragma unroll 8
         for (int y = ylo; y < yhi; ++y) {
             const float2 f = __ldg(F + (size_t)y * a.fp + x);
-            const double wy = a.pov ? 1.0 : (((double)y > cy) ? (double)(h - y) / (double)h : (double)y / (double)h);
+            const double wy = a.pov ? 1.0 : (double)(((double)y > cy) ? h - y : y) * inv_h;
             const float dyf = (float)((double)y - cy);
             const float t = __fmaf_rn(f.x, ax, __fmul_rn(__fmul_rn(f.y, wx), dyf));
             acc += (double)t * wy;
