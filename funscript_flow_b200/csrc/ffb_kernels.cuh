@@ -190,6 +190,47 @@ __device__ __forceinline__ void ffb_pyr2_level(const FfbPyr2Args& a, const float
     __syncthreads();
 }
 
+// Level 0 (3 x 3 taps, no decimation) straight from the staged window: one task = 4 adjacent outputs
+// of a row from nine 16-byte shared loads, both passes in registers, one 16-byte store.  Same
+// expressions as ffb_blur_row_t<1> / ffb_blur_col_t<1>.
+__device__ __forceinline__ void ffb_pyr2_level0(const FfbPyr2Args& a, const float* reg, int X0, int Y0, int f, int tid) {
+    const float k0 = a.taps[0].k[0], k1 = a.taps[0].k[1];
+    float* dst = a.dst[0] + (size_t)f * a.dstride[0];
+    for (int t = tid; t < PYR2_TY * (PYR2_TX / 4); t += 256) {
+        const int oy = t / (PYR2_TX / 4), ox = 4 * (t - oy * (PYR2_TX / 4));
+        const int x = X0 + ox, y = Y0 + oy;
+        if (x >= a.W || y >= a.H) continue;
+        float hrow[3][4];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const float4* p = reinterpret_cast<const float4*>(reg + (oy + PYR2_HL - 1 + r) * PYR2_RW + ox + PYR2_HL - 4);
+            const float4 q0 = p[0], q1 = p[1], q2 = p[2];          // window columns ox-4 .. ox+7
+            const float v[6] = {q0.w, q1.x, q1.y, q1.z, q1.w, q2.x};   // columns ox-1 .. ox+4
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float s = k0 * v[1 + j];
+                s += k1 * (v[j] + v[2 + j]);
+                hrow[r][j] = s;
+            }
+        }
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float s = k0 * hrow[1][j];
+            s += k1 * (hrow[0][j] + hrow[2][j]);
+            o[j] = s;
+        }
+        float* d = dst + (size_t)y * a.dp[0] + x;
+        if (x + 3 < a.W) {
+            *reinterpret_cast<float4*>(d) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (x + j < a.W) d[j] = o[j];
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) k_pyramid_pow2(FfbPyr2Args a) {
     FFB_DYN_SMEM(float, smem);
     float* reg = smem;                                  // [PYR2_RH][PYR2_RW]
@@ -218,7 +259,7 @@ __global__ void __launch_bounds__(256) k_pyramid_pow2(FfbPyr2Args a) {
         *reinterpret_cast<float4*>(reg + ry * PYR2_RW + 4 * wx) = v;
     }
     __syncthreads();
-    ffb_pyr2_level<0, 1>(a, reg, P, X0, Y0, f, tid);
+    ffb_pyr2_level0(a, reg, X0, Y0, f, tid);
     if (a.nlev > 1) ffb_pyr2_level<1, 1>(a, reg, P, X0, Y0, f, tid);
     if (a.nlev > 2) ffb_pyr2_level<2, 4>(a, reg, P, X0, Y0, f, tid);
     if (a.nlev > 3) ffb_pyr2_level<3, 9>(a, reg, P, X0, Y0, f, tid);
