@@ -29,7 +29,7 @@ _libs = {}
 
 
 def load(path: Optional[str] = None) -> C.CDLL:
-    path = os.path.abspath(path or os.environ.get("FFB_LIB") or DEFAULT_LIB)
+    path = os.path.abspath(path or DEFAULT_LIB)
     if path in _libs:
         return _libs[path]
     if not os.path.exists(path):
