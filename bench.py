@@ -268,10 +268,15 @@ def main():
                          "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
                          "alg_bytes_per_launch": it["alg_bytes"] / max(1, it["launches"]),
                          "avg_launch_ms": it["ms"] / max(1, it["launches"]), "launches": it["launches"],
+                         "timing": ("2 streams: the launch chains of the two half-batches overlap, so the time is the device "
+                                    "time of the flow phases (CUDA events on the compute stream around fork..join) and "
+                                    "achieved = bytes of all k_flow_iter launches / that time; FFB_FLOW_STREAMS=1 gives "
+                                    "per-launch times and by_level")
+                         if os.environ.get("FFB_FLOW_STREAMS", "2") != "1" else "per-launch CUDA events",
                          "by_level": {f"k{k}": {"launches": v["launches"], "ms_per_launch": v["ms"] / v["launches"],
-                                                "achieved": v["alg_bytes"] / (v["ms"] / 1000.0) / 1e9 if v["ms"] > 0 else 0.0,
-                                                "frac": (v["alg_bytes"] / (v["ms"] / 1000.0) / 1e9 / peak) if v["ms"] > 0 else 0.0}
-                                      for k, v in sorted(by_level.items())},
+                                                "achieved": v["alg_bytes"] / (v["ms"] / 1000.0) / 1e9,
+                                                "frac": v["alg_bytes"] / (v["ms"] / 1000.0) / 1e9 / peak}
+                                      for k, v in sorted(by_level.items()) if v["ms"] > 0},
                          "whole_path_bytes_per_pair": 269.7 * W * H,
                          "whole_path_frac": 269.7 * W * H * value / world / 1e9 / peak},
             "kernel_ms_per_step": kernel_ms,

@@ -182,6 +182,9 @@ struct ffb_ctx {
     int device = 0;
     std::string err;
     cudaStream_t s_comp = nullptr, s_copy = nullptr;
+    cudaStream_t s_aux[3] = {nullptr, nullptr, nullptr};   // extra streams for the sliced flow phase
+    cudaStream_t launch_stream = nullptr;              // stream of the flow-iteration launch in flight
+    cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_expand[2] = {nullptr, nullptr};
     FfbPolyConsts poly;
     // geometry
@@ -224,6 +227,10 @@ struct ffb_ctx {
     int64_t it_launches[FFB_MAX_LEVELS] = {0};          // k_flow_iter split by level k
     double it_ms[FFB_MAX_LEVELS] = {0}, it_bytes[FFB_MAX_LEVELS] = {0};
     int cur_level = -1;                                  // level k of the flow iteration being launched
+    bool phase_timing = false;                           // sliced flow phase: time the phase, not the launches
+    cudaEvent_t phase_rec_e1 = nullptr;
+    bool prof_open = false;                              // a per-launch record is waiting for its end event
+    int flow_streams = 2;
     int64_t launches = 0;
     cudaEvent_t timers[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
@@ -285,7 +292,7 @@ void prof_begin(ffb_ctx* c, int kid, double bytes) {
     c->k_bytes[kid] += bytes;
     const int lvl = (kid == FFB_K_FLOW_ITER && c->cur_level >= 0 && c->cur_level < FFB_MAX_LEVELS) ? c->cur_level : -1;
     if (lvl >= 0) { c->it_launches[lvl]++; c->it_bytes[lvl] += bytes; }
-    if (!c->prof) return;
+    if (!c->prof || (kid == FFB_K_FLOW_ITER && c->phase_timing)) return;
     ProfRec r;
     r.kid = kid;
     r.level = lvl;
@@ -294,13 +301,37 @@ void prof_begin(ffb_ctx* c, int kid, double bytes) {
         if (!c->ev_pool.empty()) { *e = c->ev_pool.back(); c->ev_pool.pop_back(); }
         else cudaEventCreate(e);
     }
-    cudaEventRecord(r.e0, c->s_comp);
+    cudaEventRecord(r.e0, kid == FFB_K_FLOW_ITER ? c->launch_stream : c->s_comp);
     c->recs.push_back(r);
+    c->prof_open = true;
 }
 void prof_end(ffb_ctx* c) {
-    if (!c->prof) return;
-    cudaEventRecord(c->recs.back().e1, c->s_comp);
+    if (!c->prof_open) return;          // prof_begin did not open a per-launch record
+    c->prof_open = false;
+    cudaEventRecord(c->recs.back().e1, c->recs.back().kid == FFB_K_FLOW_ITER ? c->launch_stream : c->s_comp);
 }
+// Sliced flow phase: the launch chains of the slices overlap, so per-launch event times would count
+// the same device time several times.  The phase is timed as a whole on s_comp instead
+// (fork ... join) and attributed to k_flow_iter.
+void prof_phase_begin(ffb_ctx* c) {
+    if (!c->prof) return;
+    ProfRec r;
+    r.kid = FFB_K_FLOW_ITER;
+    r.level = -1;
+    r.bytes = 0;
+    for (cudaEvent_t* e : {&r.e0, &r.e1}) {
+        if (!c->ev_pool.empty()) { *e = c->ev_pool.back(); c->ev_pool.pop_back(); }
+        else cudaEventCreate(e);
+    }
+    cudaEventRecord(r.e0, c->s_comp);
+    c->phase_rec_e1 = r.e1;
+    c->recs.push_back(r);
+}
+void prof_phase_end(ffb_ctx* c) {
+    if (!c->prof) return;
+    cudaEventRecord(c->phase_rec_e1, c->s_comp);
+}
+
 void prof_collect(ffb_ctx* c) {
     for (ProfRec& r : c->recs) {
         float ms = 0.f;
@@ -435,7 +466,7 @@ int launch_flow_iter_t(ffb_ctx* c, FfbIterArgs a, int npairs, int sh_target, dou
     // pair index varies fastest in launch order: the CTAs working on one spatial tile of consecutive
     // pairs are co-resident, so frame j+1's expansion (R1 of pair j, R0 of pair j+1) is read from
     // HBM once and hit in L2 the second time.
-    FFB_LAUNCH(kfn, dim3(npairs, gx, gy), dim3(NT), smem, c->s_comp, a);
+    FFB_LAUNCH(kfn, dim3(npairs, gx, gy), dim3(NT), smem, c->launch_stream, a);
     prof_end(c);
     CKL(c);
     return FFB_OK;
@@ -647,38 +678,80 @@ int expand_frames(ffb_ctx* c, const uint8_t* src, size_t stride, int pitch, int 
 }
 
 int flow_pairs(ffb_ctx* c, int p0, int np) {
+    c->phase_timing = false;
+    static const bool fuse_up = !(getenv("FFB_FUSE_UP") && atoi(getenv("FFB_FUSE_UP")) == 0);
+    // FFB_FLOW_STREAMS=n (1..4): the pairs of a batch are split in n slices whose launch chains run on
+    // n streams, so that the short coarse-level launches (and the tail of every launch) of one slice
+    // overlap the other slices' work.  Every buffer is indexed by pair; the slices share nothing that
+    // is written.
+    const int want_slices = c->flow_streams;
+    bool all_fused = fuse_up;
+    for (int l = 1; l < c->nlev; ++l)
+        all_fused = all_fused && c->lev[l].w == 2 * c->lev[l - 1].w && c->lev[l].h == 2 * c->lev[l - 1].h;
+    int nslice = want_slices < 1 ? 1 : (want_slices > 4 ? 4 : want_slices);
+    if (!all_fused || np < 4 * nslice) nslice = 1;
+    int soff[5];
+    for (int i = 0; i <= nslice; ++i) soff[i] = (int)((long long)np * i / nslice);
+    if (nslice > 1) {
+        prof_phase_begin(c);
+        c->phase_timing = true;
+        CK(c, cudaEventRecord(c->ev_fork, c->s_comp));
+        for (int i = 1; i < nslice; ++i) CK(c, cudaStreamWaitEvent(c->s_aux[i - 1], c->ev_fork, 0));
+    }
     for (int l = 0; l < c->nlev; ++l) {
         Level& L = c->lev[l];
         c->cur_level = L.k;
-        FfbRing R;
-        R.base = (char*)(c->R + L.r_off);
-        R.stride = c->r_slot_floats * sizeof(float);
-        R.first = p0 % c->S;
-        R.mod = c->S;
         const size_t fstride = (size_t)L.fp * L.h;
-        // A1e: fused into the first iteration when the level is an exact 2:1 refinement of the coarser
-        // one (closed-form resize taps, no table in the address chain); otherwise the table-driven
-        // k_upsample_flow runs first.  FFB_FUSE_UP=0 forces the separate kernel.
-        static const bool fuse_up = !(getenv("FFB_FUSE_UP") && atoi(getenv("FFB_FUSE_UP")) == 0);
-        UpSrc up;
-        const float2* fin = nullptr;
-        if (l > 0) {
+        const bool last = l == c->nlev - 1;
+        const float2* fin0 = nullptr;
+        const bool fused = l > 0 && fuse_up && L.w == 2 * c->lev[l - 1].w && L.h == 2 * c->lev[l - 1].h;
+        if (l > 0 && !fused) {
             Level& C = c->lev[l - 1];
-            if (fuse_up && L.w == 2 * C.w && L.h == 2 * C.h) {
-                up.src = C.fB; up.stride = (size_t)C.fp * C.h; up.sp = C.fp; up.wc = C.w; up.hc = C.h;
-            } else {
-                TRY(launch_upsample(c, C.fB, (size_t)C.fp * C.h, C.fp, C.w, C.h, L.fA, fstride, L.fp, L.w, L.h, L.uxi,
-                                    L.uxa, L.uyi, L.uya, np));
-                fin = L.fA;
+            TRY(launch_upsample(c, C.fB, (size_t)C.fp * C.h, C.fp, C.w, C.h, L.fA, fstride, L.fp, L.w, L.h, L.uxi,
+                                L.uxa, L.uyi, L.uya, np));
+            fin0 = L.fA;
+        }
+        for (int it = 0; it < FFB_ITERS; ++it) {
+            for (int sl = 0; sl < nslice; ++sl) {
+                const int off = soff[sl], cnt = soff[sl + 1] - soff[sl];
+                c->launch_stream = sl == 0 ? c->s_comp : c->s_aux[sl - 1];
+                FfbRing R;
+                R.base = (char*)(c->R + L.r_off);
+                R.stride = c->r_slot_floats * sizeof(float);
+                R.first = (p0 + off) % c->S;
+                R.mod = c->S;
+                FfbRing toB{(char*)(L.fB + (size_t)off * fstride), fstride * sizeof(float2), 0, 1 << 30};
+                FfbRing toA{(char*)(L.fA + (size_t)off * fstride), fstride * sizeof(float2), 0, 1 << 30};
+                FfbRing toRing{(char*)c->ring, c->ring_stride * sizeof(float2), (p0 + off) % c->ring_n, c->ring_n};
+                int rc;
+                if (it == 0) {
+                    UpSrc up;
+                    if (fused) {
+                        Level& C = c->lev[l - 1];
+                        up.stride = (size_t)C.fp * C.h;
+                        up.src = C.fB + (size_t)off * up.stride; up.sp = C.fp; up.wc = C.w; up.hc = C.h;
+                    }
+                    rc = launch_flow_iter(c, R, L.plane, L.rp, L.w, L.h, fin0 ? fin0 + (size_t)off * fstride : nullptr, fstride,
+                                          L.fp, toB, L.fp, cnt, &up);
+                } else if (it == 1) {
+                    rc = launch_flow_iter(c, R, L.plane, L.rp, L.w, L.h, L.fB + (size_t)off * fstride, fstride, L.fp, toA, L.fp, cnt);
+                } else {
+                    rc = launch_flow_iter(c, R, L.plane, L.rp, L.w, L.h, L.fA + (size_t)off * fstride, fstride, L.fp,
+                                          last ? toRing : toB, L.fp, cnt);
+                }
+                c->launch_stream = c->s_comp;
+    if (const char* e = getenv("FFB_FLOW_STREAMS")) c->flow_streams = atoi(e);
+                TRY(rc);
             }
         }
-        FfbRing toB{(char*)L.fB, fstride * sizeof(float2), 0, 1 << 30};
-        FfbRing toA{(char*)L.fA, fstride * sizeof(float2), 0, 1 << 30};
-        FfbRing toRing{(char*)c->ring, c->ring_stride * sizeof(float2), p0 % c->ring_n, c->ring_n};
-        const bool last = l == c->nlev - 1;
-        TRY(launch_flow_iter(c, R, L.plane, L.rp, L.w, L.h, fin, fstride, L.fp, toB, L.fp, np, &up));
-        TRY(launch_flow_iter(c, R, L.plane, L.rp, L.w, L.h, L.fB, fstride, L.fp, toA, L.fp, np));
-        TRY(launch_flow_iter(c, R, L.plane, L.rp, L.w, L.h, L.fA, fstride, L.fp, last ? toRing : toB, L.fp, np));
+    }
+    for (int i = 1; i < nslice; ++i) {
+        CK(c, cudaEventRecord(c->ev_join[i - 1], c->s_aux[i - 1]));
+        CK(c, cudaStreamWaitEvent(c->s_comp, c->ev_join[i - 1], 0));
+    }
+    if (nslice > 1) {
+        c->phase_timing = false;
+        prof_phase_end(c);
     }
     c->cur_level = -1;
     return FFB_OK;
@@ -909,6 +982,13 @@ int ffb_create(int device, ffb_ctx** out) {
         delete c;
         return rc;
     }
+    cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+    for (int i = 0; i < 3; ++i) {
+        cudaStreamCreateWithFlags(&c->s_aux[i], cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming);
+    }
+    c->launch_stream = c->s_comp;
+    if (const char* e = getenv("FFB_FLOW_STREAMS")) c->flow_streams = atoi(e);
     for (int b = 0; b < 2; ++b) {
         cudaEventCreateWithFlags(&c->ev_h2d[b], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&c->ev_expand[b], cudaEventDisableTiming);
@@ -938,6 +1018,8 @@ void ffb_destroy(ffb_ctx* c) {
         cudaEventDestroy(c->ev_h2d[b]); cudaEventDestroy(c->ev_expand[b]);
         cudaEventDestroy(c->ev_ch2d[b]); cudaEventDestroy(c->ev_pre[b]);
     }
+    cudaEventDestroy(c->ev_fork);
+    for (int i = 0; i < 3; ++i) { cudaEventDestroy(c->ev_join[i]); cudaStreamDestroy(c->s_aux[i]); }
     cudaStreamDestroy(c->s_comp);
     cudaStreamDestroy(c->s_copy);
     delete c;
