@@ -25,7 +25,7 @@ import numpy as np
 from . import _native
 
 DEFAULT_CUT_THRESHOLD = 7          # F:876
-DEFAULT_BATCH_FRAMES = 16
+DEFAULT_BATCH_FRAMES = 64
 
 _contexts: Dict[int, _native.FlowContext] = {}
 

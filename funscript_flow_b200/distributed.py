@@ -62,7 +62,7 @@ def process_frames_sharded(frames: Sequence[np.ndarray], fps: float, params: Dic
     mine = {}
     for i in my_brackets(ranges, rank, ws):
         a, b = ranges[i]
-        r = api.process_bracket(frames[a:b], params, ctx=ctx, batch_frames=int(params.get("gpu_batch_frames", 16)))
+        r = api.process_bracket(frames[a:b], params, ctx=ctx, batch_frames=int(params.get("gpu_batch_frames", api.DEFAULT_BATCH_FRAMES)))
         mine[i] = (r["scalar"], r["cut"], idx[a:b - 1])
     merged = {}
     for part in gather_objects(mine):

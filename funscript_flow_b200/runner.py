@@ -49,7 +49,7 @@ def process_frames(frames: Sequence[np.ndarray], fps: float, params: Dict, frame
     for a, b in _brackets(n, bracket):
         if cancel_flag and cancel_flag():
             return None
-        r = api.process_bracket(frames[a:b], params, ctx=ctx, batch_frames=int(params.get("gpu_batch_frames", 16)))
+        r = api.process_bracket(frames[a:b], params, ctx=ctx, batch_frames=int(params.get("gpu_batch_frames", api.DEFAULT_BATCH_FRAMES)))
         values.extend(r["scalar"].tolist())
         cuts.extend(r["cut"].tolist())
         stamps.extend(idx[a:b - 1])          # F:1151: frame index of the first frame of each pair
