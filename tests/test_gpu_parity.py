@@ -56,6 +56,36 @@ def test_batch_independence_1080p(gpu_ctx):
     pc.check_batch_independence(gpu_ctx, 1920, 1080, n_frames=20)
 
 
+def test_reduction_properties_at_full_size(gpu_ctx):
+    """Size-independent properties at the largest BASELINE frame (5760x2880), where a CPU comparison of
+    every pixel is still cheap for the reductions: linearity of the radial mean and of the mean magnitude,
+    sign / offset invariances of the divergence argmax, and agreement with the oracle."""
+    h, w = 2880, 5760
+    rng = np.random.default_rng(21)
+    base = np.zeros((h, w, 2), np.float32)
+    ys, xs = np.mgrid[0:h, 0:w].astype(np.float32)
+    base[..., 0] = 0.002 * (xs - 3000) + 0.3 * np.sin(ys / 97.0)
+    base[..., 1] = 0.002 * (ys - 1300) + 0.3 * np.cos(xs / 131.0)
+    base += rng.standard_normal(base.shape).astype(np.float32) * 0.01
+    base[1717, 4001, 0] += 3.0                      # an unmistakable divergence peak (rows 1716 / 1718 see it)
+    c = (3000.25, 1300.5)
+    r1 = gpu_ctx.radial_motion(base, c, False)
+    r2 = gpu_ctx.radial_motion(2.0 * base, c, False)
+    assert abs(r2 - 2.0 * r1) <= 1e-9 * abs(r1)                         # exact scaling by 2 in every fp32 term
+    ref = mo.radial_motion_weighted(base, c, False)
+    assert abs(r1 - ref) <= 1e-6 * abs(ref)
+    other = rng.standard_normal(base.shape).astype(np.float32) * 0.05
+    rs = gpu_ctx.radial_motion(base + other, c, False)
+    assert abs(rs - (r1 + gpu_ctx.radial_motion(other, c, False))) <= 1e-5 * abs(r1)
+    assert gpu_ctx.radial_motion(base, c, True) == 0.0
+    x, y, v = gpu_ctx.max_divergence(base)
+    assert (x, y, v) == mo.max_divergence(base)                        # bit-exact on equal input
+    x2, y2, v2 = gpu_ctx.max_divergence(-base)
+    assert (x2, y2) == (x, y) and v2 == -v
+    m1, m2 = gpu_ctx.mean_magnitude(base), gpu_ctx.mean_magnitude(2.0 * base)
+    assert abs(m2 - 2.0 * m1) <= 2e-7 * m2 and abs(m1 - mo.mean_magnitude(base)) <= 2e-6 * m1
+
+
 def test_streaming_paths_agree(gpu_ctx):
     """Stream / event plumbing under real asynchrony: a 150-frame bracket pushed (a) from pageable memory
     in 3-frame batches through the pinned double buffer, (b) from pinned memory in ragged pieces, (c) from
