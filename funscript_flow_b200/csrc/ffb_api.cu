@@ -17,6 +17,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <limits>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -226,6 +227,11 @@ struct ffb_ctx {
     double k_ms[FFB_K_COUNT] = {0}, k_bytes[FFB_K_COUNT] = {0};
     int64_t it_launches[FFB_MAX_LEVELS] = {0};          // k_flow_iter split by level k
     double it_ms[FFB_MAX_LEVELS] = {0}, it_bytes[FFB_MAX_LEVELS] = {0};
+    // cudaFuncSetAttribute is per device: remember per context which kernels already had their
+    // dynamic shared-memory limit raised (a process may own contexts on several GPUs)
+    size_t pyr_smem_max = 48 * 1024;
+    bool attr_poly = false, attr_pyr2 = false;
+    std::set<const void*> attr_iter;                     // k_flow_iter instantiations already configured
     int cur_level = -1;                                  // level k of the flow iteration being launched
     bool phase_timing = false;                           // sliced flow phase: time the phase, not the launches
     cudaEvent_t phase_rec_e1 = nullptr;
@@ -373,10 +379,9 @@ int launch_pyramid(ffb_ctx* c, const uint8_t* src, size_t src_stride, int src_pi
     const size_t smem = ((size_t)a.p_off + (size_t)RH * PYR_TW) * sizeof(float);
     if (taps.r >= W || taps.r >= H) return fail(c, FFB_E_INVALID, "frame smaller than the blur radius");
     auto kfn = k_pyramid_level<PYR_TW, PYR_TH>;
-    static size_t smem_max = 48 * 1024;
-    if (smem > smem_max) {
+    if (smem > c->pyr_smem_max) {
         CK(c, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_max = smem;
+        c->pyr_smem_max = smem;
     }
     dim3 grid((w + PYR_TW - 1) / PYR_TW, (h + PYR_TH - 1) / PYR_TH, nframes);
     prof_begin(c, FFB_K_PYRAMID, (double)nframes * ((double)W * H + 4.0 * w * h));
@@ -391,10 +396,9 @@ int launch_polyexp(ffb_ctx* c, const float* src, size_t src_stride, int sp, int 
     FfbPolyArgs a;
     a.src = src; a.src_frame_stride = src_stride; a.sp = sp; a.w = w; a.h = h;
     a.dst = dst; a.plane = plane; a.rp = rp; a.c = c->poly;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!c->attr_poly) {
         CK(c, cudaFuncSetAttribute(k_polyexp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POLY_SMEM));
-        attr_set = true;
+        c->attr_poly = true;
     }
     dim3 grid((w + POLY_OW - 1) / POLY_OW, (h + POLY_ROWS - 1) / POLY_ROWS, nframes);
     prof_begin(c, FFB_K_POLYEXP, (double)nframes * 24.0 * w * h);
@@ -457,10 +461,9 @@ int launch_flow_iter_t(ffb_ctx* c, FfbIterArgs a, int npairs, int sh_target, dou
     const int gy = (h + a.SH - 1) / a.SH;
     auto kfn = a.up_src ? k_flow_iter<NT, U, MINB, HFIRST, true, HO> : k_flow_iter<NT, U, MINB, HFIRST, false, HO>;
     const size_t smem = ffb_flow_iter_smem<NT, U>();
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[a.up_src ? 1 : 0]) {
+    if (!c->attr_iter.count((const void*)kfn)) {
         CK(c, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[a.up_src ? 1 : 0] = true;
+        c->attr_iter.insert((const void*)kfn);
     }
     prof_begin(c, FFB_K_FLOW_ITER, bytes);
     // pair index varies fastest in launch order: the CTAs working on one spatial tile of consecutive
@@ -637,10 +640,9 @@ int launch_pyramid_pow2(ffb_ctx* c, const uint8_t* src, size_t stride, int pitch
         a.taps[k] = make_taps(ks[k], k == 0 ? 0.0 : ((double)(1 << k) - 1.0) * 0.5);
         px += (double)(W >> k) * (H >> k);
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!c->attr_pyr2) {
         CK(c, cudaFuncSetAttribute(k_pyramid_pow2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PYR2_SMEM));
-        attr_set = true;
+        c->attr_pyr2 = true;
     }
     dim3 grid((W + PYR2_TX - 1) / PYR2_TX, (H + PYR2_TY - 1) / PYR2_TY, nb);
     prof_begin(c, FFB_K_PYRAMID, (double)nb * ((double)W * H + 4.0 * px));
@@ -1034,7 +1036,13 @@ int ffb_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? FFB_OK : FF
 int ffb_configure(ffb_ctx* c, int w, int h, int batch_frames, int max_pairs) {
     if (!c) return FFB_E_INVALID;
     CK(c, cudaSetDevice(c->device));
-    return configure(c, w, h, batch_frames, max_pairs);
+    const int rc = configure(c, w, h, batch_frames, max_pairs);
+    if (rc != FFB_OK && !c->in_bracket) {   // leave no half-allocated geometry behind
+        const std::string msg = c->err;
+        free_geometry(c);
+        c->err = msg;
+    }
+    return rc;
 }
 
 int ffb_bracket_begin(ffb_ctx* c, int pov, double thr) {
