@@ -440,14 +440,27 @@ IterCfg iter_cfg() {
     return cfg;
 }
 
-template <int NT, int U, int MINB, bool HFIRST = false, int HO = 4>
+template <int NT, int U, int MINB, bool HFIRST = false, int HO = 4, bool CL = false>
 int launch_flow_iter_t(ffb_ctx* c, FfbIterArgs a, int npairs, int sh_target, double bytes) {
     const int w = a.w, h = a.h;
-    const int sw_max = (NT - 2 * FFB_WIN_R) / HO * HO;
-    const int nstrips = (w + sw_max - 1) / sw_max;
-    a.SW = ffb_round_up((w + nstrips - 1) / nstrips, HO);
-    if (a.SW > sw_max) a.SW = sw_max;
-    const int gx = (w + a.SW - 1) / a.SW;
+    int gx;
+    if (CL) {
+        // two CTAs per cluster: 2*NT matrix columns -> 2*SW outputs with SW <= NT - 7
+        const int sw_max = (NT - FFB_WIN_R) / HO * HO;
+        const int nclusters = (w + 2 * sw_max - 1) / (2 * sw_max);
+        a.SW = ffb_round_up((w + 2 * nclusters - 1) / (2 * nclusters), HO);
+        if (a.SW > sw_max) a.SW = sw_max;
+        gx = 2 * nclusters;
+        // the row buffer holds NT + 16 positions: the seam offset NT - SW must stay within 16 columns;
+        // widths that do not split into such clusters use the plain kernel
+        if (a.SW < NT - 16) return launch_flow_iter_t<NT, U, MINB, HFIRST, HO, false>(c, a, npairs, sh_target, bytes);
+    } else {
+        const int sw_max = (NT - 2 * FFB_WIN_R) / HO * HO;
+        const int nstrips = (w + sw_max - 1) / sw_max;
+        a.SW = ffb_round_up((w + nstrips - 1) / nstrips, HO);
+        if (a.SW > sw_max) a.SW = sw_max;
+        gx = (w + a.SW - 1) / a.SW;
+    }
     // Row segments depend on the level geometry only (never on the batch composition), so a pair's
     // result is bit-identical however frames are batched or sharded.
     // at most sh_target rows per segment, at least min_seg segments per level (coarse levels would
@@ -459,8 +472,8 @@ int launch_flow_iter_t(ffb_ctx* c, FfbIterArgs a, int npairs, int sh_target, dou
     if (nseg < 1) nseg = 1;
     a.SH = (h + nseg - 1) / nseg;
     const int gy = (h + a.SH - 1) / a.SH;
-    auto kfn = a.up_src ? k_flow_iter<NT, U, MINB, HFIRST, true, HO> : k_flow_iter<NT, U, MINB, HFIRST, false, HO>;
-    const size_t smem = ffb_flow_iter_smem<NT, U>();
+    auto kfn = a.up_src ? k_flow_iter<NT, U, MINB, HFIRST, true, HO, CL> : k_flow_iter<NT, U, MINB, HFIRST, false, HO, CL>;
+    const size_t smem = ffb_flow_iter_smem<NT, U, CL>();
     if (!c->attr_iter.count((const void*)kfn)) {
         CK(c, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         c->attr_iter.insert((const void*)kfn);
@@ -469,7 +482,11 @@ int launch_flow_iter_t(ffb_ctx* c, FfbIterArgs a, int npairs, int sh_target, dou
     // pair index varies fastest in launch order: the CTAs working on one spatial tile of consecutive
     // pairs are co-resident, so frame j+1's expansion (R1 of pair j, R0 of pair j+1) is read from
     // HBM once and hit in L2 the second time.
-    FFB_LAUNCH(kfn, dim3(npairs, gx, gy), dim3(NT), smem, c->launch_stream, a);
+    if (CL) {
+        FFB_LAUNCH_CLUSTER(kfn, dim3(npairs, gx, gy), dim3(NT), smem, c->launch_stream, 1, 2, 1, a);
+    } else {
+        FFB_LAUNCH(kfn, dim3(npairs, gx, gy), dim3(NT), smem, c->launch_stream, a);
+    }
     prof_end(c);
     CKL(c);
     return FFB_OK;
@@ -502,6 +519,9 @@ int launch_flow_iter(ffb_ctx* c, FfbRing R, size_t plane, int rp, int w, int h, 
         case 12824: return launch_flow_iter_t<128, 2, 4>(c, a, npairs, k.sh, bytes);             // gather first, 4 CTAs/SM
         case 12827: return launch_flow_iter_t<128, 2, 4, true, 8>(c, a, npairs, k.sh, bytes);    // hfirst, 8 outputs / task
         case 12846: return launch_flow_iter_t<128, 4, 3, true>(c, a, npairs, k.sh, bytes);       // 4 rows / step
+        case 12848: return launch_flow_iter_t<128, 4, 3, true, 4, true>(c, a, npairs, k.sh, bytes);   // clusters, 4 rows / step
+        case 12828:   // "x8": hfirst + 2-CTA clusters sharing the seam columns through DSMEM
+            return launch_flow_iter_t<128, 2, 4, true, 4, true>(c, a, npairs, k.sh, bytes);
         case 25626: return launch_flow_iter_t<256, 2, 2, true>(c, a, npairs, k.sh, bytes);       // 256-thread strips
         default:    return launch_flow_iter_t<128, 2, 4, true>(c, a, npairs, k.sh, bytes);       // 128x2, horizontal first
     }

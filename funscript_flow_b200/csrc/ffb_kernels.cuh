@@ -509,8 +509,10 @@ struct FfbIterArgs {
     const float2* up_src; size_t up_stride; int usp; int wc, hc;
 };
 
-template <int NT, int U>
-__host__ __device__ constexpr size_t ffb_flow_iter_smem() { return sizeof(float) * (2 * U * 5 * (NT + 4) + FFB_WIN * 5 * NT); }
+template <int NT, int U, bool CL = false>
+__host__ __device__ constexpr size_t ffb_flow_iter_smem() {
+    return sizeof(float) * (2 * U * 5 * (CL ? NT + 16 : NT + 4) + FFB_WIN * 5 * NT);
+}
 
 // Raw inputs of one matrix update, as loaded (all loads unconditional).
 struct FfbGather {
@@ -595,10 +597,14 @@ __device__ __forceinline__ void ffb_up2(int d, int src_n, int& i0, int& i1, floa
     i1 = min(i0 + 1, src_n - 1);
 }
 
-template <int NT, int U, int MINB, bool HFIRST, bool UP2X, int HO>
+// CL: the strips of two CTAs form a thread-block cluster that covers 2*NT contiguous matrix columns;
+// each CTA computes the vertical sums of its own NT columns only and the few columns next to the seam
+// are exchanged through distributed shared memory (each boundary thread also stores its sums into
+// the partner's row buffer), so the 14-column halo is paid once per cluster instead of once per CTA.
+template <int NT, int U, int MINB, bool HFIRST, bool UP2X, int HO, bool CL>
 __global__ void __launch_bounds__(NT, MINB) k_flow_iter(FfbIterArgs a) {
     static_assert(HO == 4 || HO == 8, "outputs per horizontal task");
-    constexpr int HP = NT + 4;
+    constexpr int HP = CL ? NT + 16 : NT + 4;
     // dynamic shared memory (exceeds the 48 KB static limit): hrow first (16-byte aligned), then ring
     FFB_DYN_SMEM(float, smem_f);
     typedef float (*HrowT)[U][5][HP];
@@ -614,8 +620,18 @@ __global__ void __launch_bounds__(NT, MINB) k_flow_iter(FfbIterArgs a) {
     const float2* fin = a.fin ? a.fin + (size_t)pair * a.fin_stride : nullptr;
     float2* fout = reinterpret_cast<float2*>(ffb_ring_at(a.fout, pair));
     const int w = a.w, h = a.h;
-    const int xo0 = blockIdx.y * a.SW;
-    const int xc = ffb_clampi(xo0 - FFB_WIN_R + tid, 0, w - 1);
+    // CL: a.SW = outputs per CTA; cluster c covers outputs [2c*SW, 2c*SW + 2*SW) and matrix columns
+    // xoc - 7 .. xoc + 2*NT - 8, CTA `crank` owning columns crank*NT .. crank*NT + NT - 1 of them
+    const unsigned crank = CL ? ffb_cluster_rank() : 0u;
+    const int xoc = CL ? (int)(blockIdx.y >> 1) * 2 * a.SW : 0;
+    const int xo0 = CL ? xoc + (int)crank * a.SW : (int)blockIdx.y * a.SW;
+    const int xc = ffb_clampi((CL ? xoc + (int)crank * NT : xo0) - FFB_WIN_R + tid, 0, w - 1);
+    // position of this thread's column in the CTA's row buffer; window of output j starts at position j
+    const int own_off = (CL && crank == 1) ? NT - a.SW : 0;
+    // seam columns: CTA 0's columns >= SW are positions tid - SW of CTA 1; CTA 1's columns < SW + 14 - NT
+    // are positions NT + tid of CTA 0
+    const bool seam = CL && (crank == 0 ? tid >= a.SW : tid < a.SW + 2 * FFB_WIN_R - NT);
+    const int seam_pos = crank == 0 ? tid - a.SW : NT + tid;
     const int y0 = blockIdx.z * a.SH;
     const int y1 = min(y0 + a.SH, h);
     const int nfeed = (y1 - y0) + 2 * FFB_WIN_R;
@@ -631,13 +647,36 @@ __global__ void __launch_bounds__(NT, MINB) k_flow_iter(FfbIterArgs a) {
     for (int s = 0; s < FFB_WIN; ++s)
 #pragma unroll
         for (int c = 0; c < 5; ++c) ring[s][c][tid] = 0.f;
-    if (tid < 4) {
+    if (!CL && tid < 4) {
 #pragma unroll
         for (int b = 0; b < 2; ++b)
 #pragma unroll
             for (int u = 0; u < U; ++u)
 #pragma unroll
                 for (int c = 0; c < 5; ++c) hrow[b][u][c][NT + tid] = 0.f;
+    }
+    if (CL) {   // positions never written by either CTA are read (not used) by the last 16-byte loads
+        if (tid < 16) {
+            const int pos = crank == 0 ? NT + tid : tid;      // CTA 0: tail beyond its columns; CTA 1: head before own_off
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) hrow[b][u][c][pos] = 0.f;
+        }
+        if (crank == 1 && tid < 16) {
+            const int pos = own_off + NT + tid;
+            if (pos < HP) {
+#pragma unroll
+                for (int b = 0; b < 2; ++b)
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+#pragma unroll
+                        for (int c = 0; c < 5; ++c) hrow[b][u][c][pos] = 0.f;
+            }
+        }
+        ffb_cluster_sync();      // the partner must not store into this buffer before it is initialised
     }
     float vs[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, comp[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     int slot = 0;
@@ -804,9 +843,13 @@ __global__ void __launch_bounds__(NT, MINB) k_flow_iter(FfbIterArgs a) {
                 slot = slot + 1 == FFB_WIN ? 0 : slot + 1;
             }
 #pragma unroll
-            for (int c = 0; c < 5; ++c) hrow[buf][u][c][tid] = vs[c];
+            for (int c = 0; c < 5; ++c) hrow[buf][u][c][own_off + tid] = vs[c];
+            if (seam) {
+#pragma unroll
+                for (int c = 0; c < 5; ++c) ffb_dsmem_store(&hrow[buf][u][c][seam_pos], crank ^ 1u, vs[c]);
+            }
         }
-        __syncthreads();
+        if (CL) ffb_cluster_sync(); else __syncthreads();
 #pragma unroll
         for (int u = 0; u < U; ++u) d[u] = dn[u];
     }

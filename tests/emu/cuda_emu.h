@@ -56,9 +56,12 @@ namespace emu {
 struct Fiber {
     ucontext_t ctx;
     char* stack = nullptr;
-    int state = 0;   // 0 runnable, 1 waiting block barrier, 2 waiting warp barrier, 3 done
+    int state = 0;   // 0 runnable, 1 waiting block barrier, 2 waiting warp barrier, 3 done, 4 waiting cluster barrier
     uint3 tid{0, 0, 0};
-    int linear = 0;
+    uint3 bid{0, 0, 0};
+    int linear = 0;  // thread index inside its CTA
+    int cta = 0;     // rank of its CTA inside the cluster
+    char* smem = nullptr;
 };
 inline uint3 g_threadIdx, g_blockIdx;
 inline dim3 g_blockDim, g_gridDim;
@@ -66,9 +69,11 @@ inline ucontext_t g_sched;
 inline Fiber* g_cur = nullptr;
 inline std::vector<Fiber> g_fibers;
 inline std::function<void()> g_body;
-inline char* g_dyn_smem = nullptr;
-inline size_t g_dyn_smem_cap = 0;
-inline unsigned long long g_warp_buf[64][32];   // shuffle exchange, up to 64 warps / block
+inline char* g_dyn_smem = nullptr;       // dynamic shared memory of the running CTA
+inline char* g_smem_pool = nullptr;      // one slice per CTA of the running cluster
+inline size_t g_smem_pool_cap = 0, g_smem_slice = 0;
+inline unsigned g_cluster_ctas = 1;
+inline unsigned long long g_warp_buf[512][32];   // shuffle exchange, per (cta, warp)
 inline long long g_launches = 0;
 constexpr size_t kStack = 256 * 1024;
 
@@ -83,16 +88,22 @@ inline void yield_state(int st) {
     swapcontext(&f->ctx, &g_sched);
     // resumed: scheduler restored the thread identity
 }
-inline void run_block(unsigned nthreads) {
-    if (g_fibers.size() < nthreads) {
+// Runs the CTAs of one cluster (ncta >= 1) to completion; `bids` holds their block indices.
+inline void run_cluster(unsigned nthreads, unsigned ncta, const uint3* bids) {
+    const unsigned total = nthreads * ncta;
+    if (g_fibers.size() < total) {
         size_t old = g_fibers.size();
-        g_fibers.resize(nthreads);
-        for (size_t i = old; i < nthreads; ++i) g_fibers[i].stack = (char*)malloc(kStack);
+        g_fibers.resize(total);
+        for (size_t i = old; i < total; ++i) g_fibers[i].stack = (char*)malloc(kStack);
     }
-    for (unsigned i = 0; i < nthreads; ++i) {
-        Fiber& f = g_fibers[i];
+    for (unsigned k = 0; k < total; ++k) {
+        Fiber& f = g_fibers[k];
+        const unsigned i = k % nthreads;
         f.state = 0;
         f.linear = (int)i;
+        f.cta = (int)(k / nthreads);
+        f.bid = bids[f.cta];
+        f.smem = g_smem_pool ? g_smem_pool + (size_t)f.cta * g_smem_slice : nullptr;
         f.tid.x = i % g_blockDim.x;
         f.tid.y = (i / g_blockDim.x) % g_blockDim.y;
         f.tid.z = i / (g_blockDim.x * g_blockDim.y);
@@ -102,40 +113,54 @@ inline void run_block(unsigned nthreads) {
         f.ctx.uc_link = &g_sched;
         makecontext(&f.ctx, (void (*)())fiber_entry, 0);
     }
+    const unsigned wpc = (nthreads + 31) / 32;
     for (;;) {
-        for (unsigned i = 0; i < nthreads; ++i) {
-            Fiber& f = g_fibers[i];
+        for (unsigned k = 0; k < total; ++k) {
+            Fiber& f = g_fibers[k];
             if (f.state != 0) continue;
             g_cur = &f;
             g_threadIdx = f.tid;
+            g_blockIdx = f.bid;
+            g_dyn_smem = f.smem;
             swapcontext(&g_sched, &f.ctx);
         }
         // every fiber is now waiting or done
-        unsigned done = 0, wblock = 0;
-        for (unsigned i = 0; i < nthreads; ++i) {
-            done += g_fibers[i].state == 3;
-            wblock += g_fibers[i].state == 1;
+        unsigned done = 0, wcluster = 0;
+        for (unsigned k = 0; k < total; ++k) {
+            done += g_fibers[k].state == 3;
+            wcluster += g_fibers[k].state == 4;
         }
-        if (done == nthreads) break;
+        if (done == total) break;
         bool released = false;
-        // warp barriers first
-        unsigned nwarps = (nthreads + 31) / 32;
-        for (unsigned w = 0; w < nwarps; ++w) {
-            unsigned lo = w * 32, hi = std::min(nthreads, lo + 32), live = 0, ww = 0;
-            for (unsigned i = lo; i < hi; ++i) {
-                live += g_fibers[i].state != 3;
-                ww += g_fibers[i].state == 2;
-            }
-            if (ww && ww == live) {
-                for (unsigned i = lo; i < hi; ++i) if (g_fibers[i].state == 2) g_fibers[i].state = 0;
-                released = true;
+        for (unsigned c = 0; c < ncta; ++c) {               // warp barriers
+            for (unsigned w = 0; w < wpc; ++w) {
+                unsigned lo = c * nthreads + w * 32, hi = std::min(c * nthreads + nthreads, lo + 32), live = 0, ww = 0;
+                for (unsigned k = lo; k < hi; ++k) {
+                    live += g_fibers[k].state != 3;
+                    ww += g_fibers[k].state == 2;
+                }
+                if (ww && ww == live) {
+                    for (unsigned k = lo; k < hi; ++k) if (g_fibers[k].state == 2) g_fibers[k].state = 0;
+                    released = true;
+                }
             }
         }
         if (!released) {
-            if (wblock + done == nthreads && wblock) {
-                for (unsigned i = 0; i < nthreads; ++i) if (g_fibers[i].state == 1) g_fibers[i].state = 0;
-                released = true;
+            for (unsigned c = 0; c < ncta; ++c) {           // block barriers, per CTA
+                unsigned live = 0, wb = 0;
+                for (unsigned k = c * nthreads; k < (c + 1) * nthreads; ++k) {
+                    live += g_fibers[k].state != 3;
+                    wb += g_fibers[k].state == 1;
+                }
+                if (wb && wb == live) {
+                    for (unsigned k = c * nthreads; k < (c + 1) * nthreads; ++k) if (g_fibers[k].state == 1) g_fibers[k].state = 0;
+                    released = true;
+                }
             }
+        }
+        if (!released && wcluster && wcluster + done == total) {   // cluster barrier
+            for (unsigned k = 0; k < total; ++k) if (g_fibers[k].state == 4) g_fibers[k].state = 0;
+            released = true;
         }
         if (!released) {
             fprintf(stderr, "cuda_emu: deadlock / divergent barrier in block (%u,%u,%u)\n", g_blockIdx.x, g_blockIdx.y, g_blockIdx.z);
@@ -143,31 +168,43 @@ inline void run_block(unsigned nthreads) {
         }
     }
 }
+// cluster = CTAs per cluster along (x, y, z); the grid must be a multiple of it
 template <class F>
-inline void launch(dim3 grid, dim3 block, size_t smem, F body) {
+inline void launch(dim3 grid, dim3 block, size_t smem, F body, dim3 cluster = dim3(1, 1, 1)) {
     ++g_launches;
-    if (smem > g_dyn_smem_cap) {
-        free(g_dyn_smem);
-        g_dyn_smem = (char*)aligned_alloc(128, (smem + 127) / 128 * 128);
-        g_dyn_smem_cap = smem;
+    const unsigned ncta = cluster.x * cluster.y * cluster.z;
+    g_smem_slice = (smem + 127) / 128 * 128;
+    if (g_smem_slice * ncta > g_smem_pool_cap) {
+        free(g_smem_pool);
+        g_smem_pool_cap = g_smem_slice * ncta;
+        g_smem_pool = (char*)aligned_alloc(128, g_smem_pool_cap);
     }
     g_body = body;
     g_gridDim = grid;
     g_blockDim = block;
-    unsigned nthreads = block.x * block.y * block.z;
-    for (unsigned bz = 0; bz < grid.z; ++bz)
-        for (unsigned by = 0; by < grid.y; ++by)
-            for (unsigned bx = 0; bx < grid.x; ++bx) {
-                g_blockIdx = uint3{bx, by, bz};
-                if (smem) memset(g_dyn_smem, 0xCD, smem);   // poison: catches reads of unwritten smem
-                run_block(nthreads);
+    g_cluster_ctas = ncta;
+    const unsigned nthreads = block.x * block.y * block.z;
+    if (grid.x % cluster.x || grid.y % cluster.y || grid.z % cluster.z) {
+        fprintf(stderr, "cuda_emu: grid is not a multiple of the cluster shape\n");
+        abort();
+    }
+    uint3 bids[16];
+    for (unsigned cz = 0; cz < grid.z; cz += cluster.z)
+        for (unsigned cy = 0; cy < grid.y; cy += cluster.y)
+            for (unsigned cx = 0; cx < grid.x; cx += cluster.x) {
+                unsigned n = 0;
+                for (unsigned z = 0; z < cluster.z; ++z)
+                    for (unsigned y = 0; y < cluster.y; ++y)
+                        for (unsigned x = 0; x < cluster.x; ++x) bids[n++] = uint3{cx + x, cy + y, cz + z};
+                if (smem) memset(g_smem_pool, 0xCD, g_smem_slice * ncta);   // poison: catches reads of unwritten smem
+                run_cluster(nthreads, ncta, bids);
             }
 }
 template <class T>
 inline T shfl_generic(T v, int src_lane) {
     static_assert(sizeof(T) <= 8, "shuffle payload");
     int lin = g_cur->linear;
-    int warp = lin / 32, lane = lin % 32;
+    int warp = g_cur->cta * 64 + lin / 32, lane = lin % 32;
     unsigned long long bits = 0;
     memcpy(&bits, &v, sizeof(T));
     g_warp_buf[warp][lane] = bits;
@@ -177,6 +214,15 @@ inline T shfl_generic(T v, int src_lane) {
     T out;
     memcpy(&out, &got, sizeof(T));
     return out;
+}
+// thread-block cluster support: rank, barrier, distributed-shared-memory address of a peer CTA
+inline unsigned cluster_rank() { return (unsigned)g_cur->cta; }
+inline void cluster_sync() { yield_state(4); }
+template <class T>
+inline T* map_shared(T* p, unsigned rank) {
+    const size_t off = (size_t)((char*)p - g_cur->smem);
+    if (off >= g_smem_slice || rank >= g_cluster_ctas) { fprintf(stderr, "cuda_emu: bad DSMEM mapping\n"); abort(); }
+    return (T*)(g_smem_pool + (size_t)rank * g_smem_slice + off);
 }
 }  // namespace emu
 

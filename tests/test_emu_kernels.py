@@ -114,3 +114,23 @@ def test_headless_folder_sharded_over_ranks(emu_ctx, tmp_path, monkeypatch):
         present = [k for k in range(3) if (tmp_path / f"v{k}.funscript").exists()]
         assert present == ([0, 2] if rank == 0 else [0, 1, 2])
     assert {k: json.load(open(str(tmp_path / f"v{k}.funscript"))) for k in range(3)} == single
+
+
+def test_cluster_variant_in_subprocess(emu_lib):
+    """The opt-in thread-block-cluster variant of k_flow_iter (two CTAs share the strip seam through
+    distributed shared memory; FFB_ITER_CFG=128x2x8 -- measured slower on B200, kept as an experiment):
+    the emulator runs both CTAs of a cluster as interleaved fibers with a cluster barrier and DSMEM."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from funscript_flow_b200 import _native\n"
+        "import parity_checks as pc\n"
+        "ctx = _native.FlowContext(0, %r)\n"
+        "print(pc.check_farneback_vs_cv2(ctx, 480, 136))\n"
+        "pc.check_batch_independence(ctx, 480, 72, n_frames=6)\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)), emu_lib)
+    env = dict(os.environ, FFB_ITER_CFG="128x2x8")
+    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout + res.stderr
