@@ -201,6 +201,7 @@ def main():
         return float(t.item())
 
     # ---- device-resident arm ("value") --------------------------------------------------------
+    r0 = None
     for _ in range(args.warmup):
         r0 = step_resident()
     fence()
@@ -231,7 +232,9 @@ def main():
     fence()
     wall_e2e = time.perf_counter() - t0
     clocks = sampler.stop()
-    assert r["n_pairs"] == P and np.array_equal(r["scalar"], r_e["scalar"]) and np.array_equal(r["scalar"], r0["scalar"])
+    # the device-resident and the end-to-end arm (and the warm-up) computed the same numbers
+    assert r["n_pairs"] == P and np.array_equal(r["scalar"], r_e["scalar"])
+    assert r0 is None or np.array_equal(r["scalar"], r0["scalar"])
 
     dev_ms = max_over_ranks(dev_ms)
     wall_e2e = max_over_ranks(wall_e2e)
