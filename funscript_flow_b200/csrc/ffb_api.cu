@@ -428,7 +428,7 @@ int launch_upsample(ffb_ctx* c, const float2* src, size_t src_stride, int sp, in
 struct IterCfg { int nt, u, minb, sh; };
 IterCfg iter_cfg() {
     static IterCfg cfg = [] {
-        IterCfg c{128, 2, 6, 180};
+        IterCfg c{128, 2, 6, 270};
         if (const char* e = getenv("FFB_ITER_CFG")) {
             int nt = 0, u = 0, m = 0;
             const int got = sscanf(e, "%dx%dx%d", &nt, &u, &m);
@@ -465,7 +465,7 @@ int launch_flow_iter_t(ffb_ctx* c, FfbIterArgs a, int npairs, int sh_target, dou
     // result is bit-identical however frames are batched or sharded.
     // at most sh_target rows per segment, at least min_seg segments per level (coarse levels would
     // otherwise be a handful of long, latency-bound marches), never under 32 rows
-    static const int min_seg = getenv("FFB_ITER_MINSEG") ? atoi(getenv("FFB_ITER_MINSEG")) : 6;
+    static const int min_seg = getenv("FFB_ITER_MINSEG") ? atoi(getenv("FFB_ITER_MINSEG")) : 4;
     int nseg = (h + sh_target - 1) / sh_target;
     if (nseg < min_seg) nseg = min_seg;
     if (nseg > (h + 31) / 32) nseg = (h + 31) / 32;
