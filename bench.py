@@ -283,6 +283,8 @@ def main():
                          "whole_path_bytes_per_pair": 269.7 * W * H,
                          "whole_path_frac": 269.7 * W * H * value / world / 1e9 / peak},
             "kernel_ms_per_step": kernel_ms,
+            "kernel_ms_note": ("CUDA-event time per kernel class; with 2 flow streams k_flow_iter is the flow-phase time and "
+                               "k_divmag (launched per slice, overlapping the other slice's flow tail) includes that overlap"),
             "wall_ms_per_step_resident": 1000 * wall_res / args.steps,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -185,6 +185,9 @@ struct ffb_ctx {
     cudaStream_t s_comp = nullptr, s_copy = nullptr;
     cudaStream_t s_aux[3] = {nullptr, nullptr, nullptr};   // extra streams for the sliced flow phase
     cudaStream_t launch_stream = nullptr;              // stream of the flow-iteration launch in flight
+    cudaStream_t aux_stream = nullptr;                 // stream of the divergence / magnitude launch in flight
+    cudaStream_t s_time = nullptr;                     // only carries the end-of-flow-phase timing event
+    cudaEvent_t ev_flow_end[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_expand[2] = {nullptr, nullptr};
     FfbPolyConsts poly;
@@ -234,6 +237,7 @@ struct ffb_ctx {
     std::set<const void*> attr_iter;                     // k_flow_iter instantiations already configured
     int cur_level = -1;                                  // level k of the flow iteration being launched
     bool phase_timing = false;                           // sliced flow phase: time the phase, not the launches
+    bool sliced_divmag = false;                          // flow_pairs already launched k_divmag per slice
     cudaEvent_t phase_rec_e1 = nullptr;
     bool prof_open = false;                              // a per-launch record is waiting for its end event
     int flow_streams = 2;
@@ -307,14 +311,15 @@ void prof_begin(ffb_ctx* c, int kid, double bytes) {
         if (!c->ev_pool.empty()) { *e = c->ev_pool.back(); c->ev_pool.pop_back(); }
         else cudaEventCreate(e);
     }
-    cudaEventRecord(r.e0, kid == FFB_K_FLOW_ITER ? c->launch_stream : c->s_comp);
+    cudaEventRecord(r.e0, kid == FFB_K_FLOW_ITER ? c->launch_stream : (kid == FFB_K_DIVMAG ? c->aux_stream : c->s_comp));
     c->recs.push_back(r);
     c->prof_open = true;
 }
 void prof_end(ffb_ctx* c) {
     if (!c->prof_open) return;          // prof_begin did not open a per-launch record
     c->prof_open = false;
-    cudaEventRecord(c->recs.back().e1, c->recs.back().kid == FFB_K_FLOW_ITER ? c->launch_stream : c->s_comp);
+    const int kid_ = c->recs.back().kid;
+    cudaEventRecord(c->recs.back().e1, kid_ == FFB_K_FLOW_ITER ? c->launch_stream : (kid_ == FFB_K_DIVMAG ? c->aux_stream : c->s_comp));
 }
 // Sliced flow phase: the launch chains of the slices overlap, so per-launch event times would count
 // the same device time several times.  The phase is timed as a whole on s_comp instead
@@ -333,9 +338,13 @@ void prof_phase_begin(ffb_ctx* c) {
     c->phase_rec_e1 = r.e1;
     c->recs.push_back(r);
 }
-void prof_phase_end(ffb_ctx* c) {
+// the phase ends when the last slice's last flow iteration does: a side stream waits for every slice's
+// end-of-flow event and records the timing event, so that the per-slice reductions that follow on the
+// slice streams are not counted
+void prof_phase_end(ffb_ctx* c, int nslice) {
     if (!c->prof) return;
-    cudaEventRecord(c->phase_rec_e1, c->s_comp);
+    for (int i = 0; i < nslice; ++i) cudaStreamWaitEvent(c->s_time, c->ev_flow_end[i], 0);
+    cudaEventRecord(c->phase_rec_e1, c->s_time);
 }
 
 void prof_collect(ffb_ctx* c) {
@@ -699,6 +708,8 @@ int expand_frames(ffb_ctx* c, const uint8_t* src, size_t stride, int pitch, int 
     return FFB_OK;
 }
 
+int launch_divmag(ffb_ctx* c, int p0, int off, int cnt, cudaStream_t stream);
+
 int flow_pairs(ffb_ctx* c, int p0, int np) {
     c->phase_timing = false;
     static const bool fuse_up = !(getenv("FFB_FUSE_UP") && atoi(getenv("FFB_FUSE_UP")) == 0);
@@ -762,34 +773,49 @@ int flow_pairs(ffb_ctx* c, int p0, int np) {
                                           last ? toRing : toB, L.fp, cnt);
                 }
                 c->launch_stream = c->s_comp;
+    c->aux_stream = c->s_comp;
     if (const char* e = getenv("FFB_FLOW_STREAMS")) c->flow_streams = atoi(e);
                 TRY(rc);
             }
         }
     }
+    if (nslice > 1) {
+        c->phase_timing = false;
+        for (int sl = 0; sl < nslice; ++sl) CK(c, cudaEventRecord(c->ev_flow_end[sl], sl == 0 ? c->s_comp : c->s_aux[sl - 1]));
+        prof_phase_end(c, nslice);
+        // each slice reduces its own pairs as soon as its chain is done (overlaps the other slice's tail)
+        for (int sl = 0; sl < nslice; ++sl)
+            TRY(launch_divmag(c, p0, soff[sl], soff[sl + 1] - soff[sl], sl == 0 ? c->s_comp : c->s_aux[sl - 1]));
+    }
     for (int i = 1; i < nslice; ++i) {
         CK(c, cudaEventRecord(c->ev_join[i - 1], c->s_aux[i - 1]));
         CK(c, cudaStreamWaitEvent(c->s_comp, c->ev_join[i - 1], 0));
     }
-    if (nslice > 1) {
-        c->phase_timing = false;
-        prof_phase_end(c);
-    }
+    c->sliced_divmag = nslice > 1;
     c->cur_level = -1;
     return FFB_OK;
 }
 
-int phase1_reduce(ffb_ctx* c, int p0, int np) {
+// divergence / magnitude partials of `cnt` pairs starting at pair p0 + off of the bracket, on `stream`
+int launch_divmag(ffb_ctx* c, int p0, int off, int cnt, cudaStream_t stream) {
     FfbDivArgs d;
-    d.flow = FfbRing{(char*)c->ring, c->ring_stride * sizeof(float2), p0 % c->ring_n, c->ring_n};
+    d.flow = FfbRing{(char*)c->ring, c->ring_stride * sizeof(float2), (p0 + off) % c->ring_n, c->ring_n};
     d.fp = c->fp0; d.w = c->W; d.h = c->H; d.rows_per_block = c->div_rpb;
-    d.pkey = c->d_pkey; d.psum = c->d_psum;
-    prof_begin(c, FFB_K_DIVMAG, (double)np * 8.0 * c->W * c->H);
-    FFB_LAUNCH(k_divmag, dim3(c->div_gx, c->div_gy, np), dim3(256), 0, c->s_comp, d);
+    d.pkey = c->d_pkey + (size_t)off * c->div_nblk;
+    d.psum = c->d_psum + (size_t)off * c->div_nblk;
+    c->aux_stream = stream;
+    prof_begin(c, FFB_K_DIVMAG, (double)cnt * 8.0 * c->W * c->H);
+    FFB_LAUNCH(k_divmag, dim3(c->div_gx, c->div_gy, cnt), dim3(256), 0, stream, d);
     prof_end(c);
+    c->aux_stream = c->s_comp;
     CKL(c);
+    return FFB_OK;
+}
+
+int launch_phase1_finish(ffb_ctx* c, int p0, int np) {
     FfbP1Args f;
-    f.flow = d.flow; f.fp = c->fp0; f.w = c->W; f.h = c->H;
+    f.flow = FfbRing{(char*)c->ring, c->ring_stride * sizeof(float2), p0 % c->ring_n, c->ring_n};
+    f.fp = c->fp0; f.w = c->W; f.h = c->H;
     f.pkey = c->d_pkey; f.psum = c->d_psum; f.nblk = c->div_nblk;
     f.pov = c->pov; f.cut_threshold = c->thr; f.out0 = p0;
     f.cx = c->d_cx; f.cy = c->d_cy; f.val = c->d_val; f.mean_mag = c->d_mm; f.cut = c->d_cut;
@@ -798,6 +824,11 @@ int phase1_reduce(ffb_ctx* c, int p0, int np) {
     prof_end(c);
     CKL(c);
     return FFB_OK;
+}
+
+int phase1_reduce(ffb_ctx* c, int p0, int np) {
+    TRY(launch_divmag(c, p0, 0, np, c->s_comp));
+    return launch_phase1_finish(c, p0, np);
 }
 
 // radial pass for bracket pairs [j0, j1); n = number of pairs known so far (window truncation)
@@ -878,7 +909,8 @@ int process_batch(ffb_ctx* c, const uint8_t* frames, int nb, size_t pitch, size_
         const int p0 = c->pairs_done;
         if (p0 + np > c->maxPairs) return fail(c, FFB_E_INVALID, "bracket exceeds max_bracket_pairs=%d", c->maxPairs);
         TRY(flow_pairs(c, p0, np));
-        TRY(phase1_reduce(c, p0, np));
+        if (c->sliced_divmag) TRY(launch_phase1_finish(c, p0, np));
+        else TRY(phase1_reduce(c, p0, np));
         c->pairs_done += np;
         const int r1 = c->pairs_done - 6;
         if (r1 > c->radial_done) {
@@ -1005,11 +1037,14 @@ int ffb_create(int device, ffb_ctx** out) {
         return rc;
     }
     cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+    cudaStreamCreateWithFlags(&c->s_time, cudaStreamNonBlocking);
+    for (int i = 0; i < 4; ++i) cudaEventCreateWithFlags(&c->ev_flow_end[i], cudaEventDisableTiming);
     for (int i = 0; i < 3; ++i) {
         cudaStreamCreateWithFlags(&c->s_aux[i], cudaStreamNonBlocking);
         cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming);
     }
     c->launch_stream = c->s_comp;
+    c->aux_stream = c->s_comp;
     if (const char* e = getenv("FFB_FLOW_STREAMS")) c->flow_streams = atoi(e);
     for (int b = 0; b < 2; ++b) {
         cudaEventCreateWithFlags(&c->ev_h2d[b], cudaEventDisableTiming);
@@ -1041,6 +1076,8 @@ void ffb_destroy(ffb_ctx* c) {
         cudaEventDestroy(c->ev_ch2d[b]); cudaEventDestroy(c->ev_pre[b]);
     }
     cudaEventDestroy(c->ev_fork);
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(c->ev_flow_end[i]);
+    cudaStreamDestroy(c->s_time);
     for (int i = 0; i < 3; ++i) { cudaEventDestroy(c->ev_join[i]); cudaStreamDestroy(c->s_aux[i]); }
     cudaStreamDestroy(c->s_comp);
     cudaStreamDestroy(c->s_copy);
