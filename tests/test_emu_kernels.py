@@ -134,3 +134,34 @@ def test_cluster_variant_in_subprocess(emu_lib):
     env = dict(os.environ, FFB_ITER_CFG="128x2x8")
     res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout + res.stderr
+
+
+def test_error_paths_and_strided_input(emu_ctx):
+    """Host logic of the C ABI: calls out of sequence and out-of-range requests fail with the documented
+    codes (no exceptions swallowed, no fallback); frames given as a strided view (pitch > width) are
+    handled like contiguous ones."""
+    from funscript_flow_b200 import _native
+    clip = make_clip(96, 64, 6, seed=3)
+    emu_ctx.configure(96, 64, 2, 3)
+    with pytest.raises(_native.FFBError) as ei:
+        emu_ctx.bracket_push(clip[:2])                       # no bracket open
+    assert ei.value.code == -1
+    emu_ctx.bracket_begin(False, 7.0)
+    with pytest.raises(_native.FFBError) as ei:
+        emu_ctx.bracket_push(clip)                           # 5 pairs > max_bracket_pairs = 3
+    assert ei.value.code == -1 and "max_bracket_pairs" in str(ei.value)
+    emu_ctx.bracket_finish()
+    ref = api.process_bracket(clip, {}, ctx=emu_ctx, batch_frames=3, return_flows=True)
+    with pytest.raises(_native.FFBError) as ei:
+        emu_ctx.get_flow(99)
+    assert ei.value.code == -5
+    big = np.zeros((6, 80, 128), np.uint8)
+    big[:, 8:72, 16:112] = clip
+    view = big[:, 8:72, 16:112]                              # pitch 128, frame stride 80 * 128
+    assert not view.flags["C_CONTIGUOUS"]
+    emu_ctx.configure(96, 64, 3, 5)
+    emu_ctx.bracket_begin(False, 7.0)
+    emu_ctx.bracket_push(view)
+    got = emu_ctx.bracket_finish()
+    for k in ("scalar", "cx", "cy", "val", "mean_mag"):
+        assert np.array_equal(ref[k], got[k]), k
