@@ -2,6 +2,7 @@
 
     python -m funscript_flow_b200 INPUT [--threads N] [--detrend_window S] [--norm_window S] [--batch_size N]
                                   [--overwrite] [--vr_mode] [--pov_mode] [--disable_keyframe_reduction]
+                                  [--native_resolution] [--vr_eye left|right]      (extensions)
 
 Under `torchrun --nproc-per-node N` every rank takes each N-th video of the folder on its own GPU.
 The reference's quirk is kept: `--disable_keyframe_reduction` is a store_false flag whose
@@ -28,12 +29,15 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--pov_mode", action="store_true")
     p.add_argument("--disable_keyframe_reduction", action="store_false")
     p.add_argument("--backend", default="CUDA", help="accepted for compatibility; there is one backend")
+    # extensions the reference has no equivalent of (runner.preprocess_plan)
+    p.add_argument("--native_resolution", action="store_true", help="run the flow on the decoded frame size instead of 256x256")
+    p.add_argument("--vr_eye", choices=["left", "right"], default="left", help="which eye of a side-by-side VR frame (with --vr_mode)")
     return p
 
 
 def settings_from_args(args) -> dict:
-    """The settings dict of F:2654-2664 (same keys)."""
-    return {
+    """The settings dict of F:2654-2664 (same keys; the extension keys appear only when used)."""
+    settings = {
         "threads": args.threads,
         "detrend_window": args.detrend_window,
         "norm_window": args.norm_window,
@@ -44,6 +48,11 @@ def settings_from_args(args) -> dict:
         "keyframe_reduction": not args.disable_keyframe_reduction,
         "backend": "CUDA",
     }
+    if getattr(args, "native_resolution", False):
+        settings["native_resolution"] = True
+    if getattr(args, "vr_eye", "left") != "left":
+        settings["vr_eye"] = args.vr_eye
+    return settings
 
 
 def main(argv=None) -> int:

@@ -67,6 +67,8 @@ def load(path: Optional[str] = None) -> C.CDLL:
         "ffb_preprocess_configure": (i32, [vp, i32, i32, i32]),
         "ffb_bracket_push_bgr": (i32, [vp, vp, i32, sz, sz]),
         "ffb_stage_preprocess": (i32, [vp, u8p, i32, i32, sz, i32, u8p]),
+        "ffb_preprocess_configure_window": (i32, [vp] + [i32] * 8),
+        "ffb_stage_preprocess_window": (i32, [vp, u8p, i32, i32, sz] + [i32] * 6 + [u8p]),
         "ffb_profile": (i32, [vp, i32]),
         "ffb_profile_reset": (i32, [vp]),
         "ffb_kernel_stats": (i32, [vp, i32, C.POINTER(C.c_int64), f64p, f64p]),
@@ -200,6 +202,11 @@ class FlowContext:
         """Source geometry of decoded BGR frames for bracket_push_bgr (output is always 256x256)."""
         self._ck(self._lib.ffb_preprocess_configure(self._h, int(src_width), int(src_height), int(bool(vr_mode))))
 
+    def preprocess_configure_window(self, src_width: int, src_height: int, target, window):
+        """General form (row N4): resize to target=(w, h), keep window=(x, y, w, h) of the resized frame."""
+        self._ck(self._lib.ffb_preprocess_configure_window(self._h, int(src_width), int(src_height), int(target[0]), int(target[1]),
+                                                           *(int(v) for v in window)))
+
     def bracket_push_bgr(self, frames: np.ndarray):
         """frames: uint8 [n, H, W, 3] (or [H, W, 3]) BGR as decoded; resized + gray-converted on the GPU."""
         if frames.ndim == 3:
@@ -215,6 +222,14 @@ class FlowContext:
         h, w = bgr.shape[:2]
         out = np.empty((256, 256), np.uint8)
         self._ck(self._lib.ffb_stage_preprocess(self._h, _u8(bgr), w, h, w * 3, int(bool(vr_mode)), _u8(out)))
+        return out
+
+    def stage_preprocess_window(self, bgr: np.ndarray, target, window) -> np.ndarray:
+        bgr = np.ascontiguousarray(bgr, dtype=np.uint8)
+        h, w = bgr.shape[:2]
+        out = np.empty((int(window[3]), int(window[2])), np.uint8)
+        self._ck(self._lib.ffb_stage_preprocess_window(self._h, _u8(bgr), w, h, w * 3, int(target[0]), int(target[1]),
+                                                       *(int(v) for v in window), _u8(out)))
         return out
 
     def bracket_finish(self):

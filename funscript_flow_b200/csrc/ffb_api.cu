@@ -211,7 +211,10 @@ struct ffb_ctx {
     int div_nblk = 0, div_rpb = 0, div_gx = 0, div_gy = 0, rad_gx = 0, rad_gy = 0, rad_rpb = 0;
     char* h_res = nullptr;    // pinned result staging
     // frame pre-processing (row N2): source geometry, tables, chunked colour staging
-    int pre_W = 0, pre_H = 0, pre_vr = 0, pre_T = 0;      // pre_T = resize target (256 or 512)
+    // source size -> resize target (TW x TH) -> kept window [y0, y0+OH) x [x0, x0+OW) of the target
+    struct PrePlan { int W = 0, H = 0, TW = 0, TH = 0, x0 = 0, y0 = 0, OW = 0, OH = 0;
+                     bool operator==(const PrePlan& o) const {
+                         return W == o.W && H == o.H && TW == o.TW && TH == o.TH && x0 == o.x0 && y0 == o.y0 && OW == o.OW && OH == o.OH; } } pre;
     int *pre_xt = nullptr, *pre_yt = nullptr;
     uint8_t* d_color[2] = {nullptr, nullptr};
     uint8_t* h_color[2] = {nullptr, nullptr};
@@ -982,22 +985,34 @@ void free_preprocess(ffb_ctx* c) {
         if (c->h_color[b]) cudaFreeHost(c->h_color[b]);
         c->h_color[b] = nullptr;
     }
-    c->pre_W = c->pre_H = 0;
+    c->pre = ffb_ctx::PrePlan();
 }
 
-int launch_preprocess(ffb_ctx* c, const uint8_t* src, size_t stride, int pitch, uint8_t* dst, size_t dstride, int dpitch,
-                      const int* xt, const int* yt, int T, int vr, int W, int H, int n) {
+int launch_preprocess(ffb_ctx* c, const uint8_t* src, size_t stride, int pitch, uint8_t* dst, const ffb_ctx::PrePlan& p,
+                      const int* xt, const int* yt, int n) {
     FfbPreArgs a;
     a.src = src; a.src_frame_stride = stride; a.src_pitch = pitch;
-    a.dst = dst; a.dst_frame_stride = dstride; a.dst_pitch = dpitch;
-    a.xt = xt; a.yt = yt; a.TW = T; a.TH = T; a.y_off = vr ? T / 2 : 0;
+    a.dst = dst; a.dst_frame_stride = (size_t)p.OW * p.OH; a.dst_pitch = p.OW;
+    a.xt = xt; a.yt = yt; a.TW = p.TW; a.TH = p.TH; a.x_off = p.x0; a.y_off = p.y0; a.OW = p.OW; a.OH = p.OH;
     // algorithmic bytes: the 2x2 footprint of every output pixel (3 bytes each) + the gray output
-    prof_begin(c, FFB_K_PREPROC, (double)n * (PRE_OUT * PRE_OUT * 13.0));
-    FFB_LAUNCH(k_preprocess, dim3(PRE_OUT / 32, PRE_OUT / 8, n), dim3(256), 0, c->s_comp, a);
+    prof_begin(c, FFB_K_PREPROC, (double)n * ((double)p.OW * p.OH * 13.0));
+    FFB_LAUNCH(k_preprocess, dim3((p.OW + 31) / 32, (p.OH + 7) / 8, n), dim3(256), 0, c->s_comp, a);
     prof_end(c);
     CKL(c);
-    (void)W; (void)H;
     return FFB_OK;
+}
+
+// the reference's two modes (F:1057, F:1076-1079) as plans
+ffb_ctx::PrePlan reference_plan(int W, int H, int vr) {
+    ffb_ctx::PrePlan p;
+    p.W = W; p.H = H; p.OW = p.OH = PRE_OUT;
+    p.TW = p.TH = vr ? 2 * PRE_OUT : PRE_OUT;
+    p.x0 = 0; p.y0 = vr ? PRE_OUT : 0;
+    return p;
+}
+bool plan_ok(const ffb_ctx::PrePlan& p) {
+    return p.W >= 2 && p.H >= 2 && p.TW >= 1 && p.TH >= 1 && p.OW >= 1 && p.OH >= 1 && p.x0 >= 0 && p.y0 >= 0 &&
+           p.x0 + p.OW <= p.TW && p.y0 + p.OH <= p.TH;
 }
 
 // ======================================================================================
@@ -1435,18 +1450,17 @@ int ffb_stage_upsample_flow(ffb_ctx* c, const float* flow_c, int wc, int hc, int
 }
 
 // ---- frame pre-processing (row N2) --------------------------------------------------------
-int ffb_preprocess_configure(ffb_ctx* c, int W, int H, int vr) {
-    if (!c || W < 2 || H < 2) return fail(c, FFB_E_INVALID, "ffb_preprocess_configure: bad geometry");
+static int preprocess_configure_plan(ffb_ctx* c, const ffb_ctx::PrePlan& p) {
+    if (!c || !plan_ok(p)) return fail(c, FFB_E_INVALID, "ffb_preprocess_configure: bad geometry");
     CK(c, cudaSetDevice(c->device));
     if (c->in_bracket) return fail(c, FFB_E_INVALID, "ffb_preprocess_configure inside a bracket");
-    if (c->pre_W == W && c->pre_H == H && c->pre_vr == (vr ? 1 : 0)) return FFB_OK;
+    if (c->pre == p) return FFB_OK;
     CK(c, cudaStreamSynchronize(c->s_comp));
     CK(c, cudaStreamSynchronize(c->s_copy));
     free_preprocess(c);
-    const int T = vr ? 2 * PRE_OUT : PRE_OUT;
-    TRY(upload_vec(c, &c->pre_xt, make_u8_resize_table(T, W, true)));
-    TRY(upload_vec(c, &c->pre_yt, make_u8_resize_table(T, H, false)));
-    const size_t cbytes = (size_t)PRE_CHUNK * W * H * 3;
+    TRY(upload_vec(c, &c->pre_xt, make_u8_resize_table(p.TW, p.W, true)));
+    TRY(upload_vec(c, &c->pre_yt, make_u8_resize_table(p.TH, p.H, false)));
+    const size_t cbytes = (size_t)PRE_CHUNK * p.W * p.H * 3;
     for (int b = 0; b < 2; ++b) {
         TRY(dev_alloc(c, &c->d_color[b], cbytes));
         void* hp = nullptr;
@@ -1454,19 +1468,31 @@ int ffb_preprocess_configure(ffb_ctx* c, int W, int H, int vr) {
             return fail(c, FFB_E_NOMEM, "cudaHostAlloc(%zu) failed", cbytes);
         c->h_color[b] = (uint8_t*)hp;
     }
-    c->pre_W = W; c->pre_H = H; c->pre_vr = vr ? 1 : 0; c->pre_T = T;
+    c->pre = p;
     return FFB_OK;
+}
+int ffb_preprocess_configure(ffb_ctx* c, int W, int H, int vr) {
+    return preprocess_configure_plan(c, reference_plan(W, H, vr));
+}
+int ffb_preprocess_configure_window(ffb_ctx* c, int W, int H, int target_w, int target_h, int win_x, int win_y, int win_w,
+                                    int win_h) {
+    ffb_ctx::PrePlan p;
+    p.W = W; p.H = H; p.TW = target_w; p.TH = target_h; p.x0 = win_x; p.y0 = win_y; p.OW = win_w; p.OH = win_h;
+    return preprocess_configure_plan(c, p);
 }
 
 int ffb_bracket_push_bgr(ffb_ctx* c, const uint8_t* bgr, int n, size_t pitch, size_t stride) {
     if (!c || !c->in_bracket) return fail(c, FFB_E_INVALID, "ffb_bracket_push_bgr outside a bracket");
-    if (c->pre_W == 0) return fail(c, FFB_E_INVALID, "ffb_bracket_push_bgr before ffb_preprocess_configure");
-    if (c->W != PRE_OUT || c->H != PRE_OUT) return fail(c, FFB_E_INVALID, "pre-processed frames are 256x256: ffb_configure(ctx, 256, 256, ...)");
-    const size_t row = (size_t)c->pre_W * 3;
-    if (!bgr || n < 0 || pitch < row || stride < pitch * (size_t)(c->pre_H - 1) + row)
+    const ffb_ctx::PrePlan& pp = c->pre;
+    if (pp.W == 0) return fail(c, FFB_E_INVALID, "ffb_bracket_push_bgr before ffb_preprocess_configure");
+    if (c->W != pp.OW || c->H != pp.OH)
+        return fail(c, FFB_E_INVALID, "pre-processed frames are %dx%d: ffb_configure(ctx, %d, %d, ...)", pp.OW, pp.OH, pp.OW, pp.OH);
+    const size_t row = (size_t)pp.W * 3;
+    const size_t obytes = (size_t)pp.OW * pp.OH;
+    if (!bgr || n < 0 || pitch < row || stride < pitch * (size_t)(pp.H - 1) + row)
         return fail(c, FFB_E_INVALID, "ffb_bracket_push_bgr: bad arguments");
     const PtrKind kind = classify(bgr);
-    const size_t fbytes = row * c->pre_H;
+    const size_t fbytes = row * pp.H;
     for (int i = 0; i < n;) {
         int cap = c->frames_seen == 0 ? c->B + 1 : c->B;
         if (c->frames_seen == 0 && kind != PTR_DEVICE && c->B >= 8) cap = c->B / 4 + 1;
@@ -1488,7 +1514,7 @@ int ffb_bracket_push_bgr(ffb_ctx* c, const uint8_t* bgr, int n, size_t pitch, si
                         const uint8_t* s0 = src + (size_t)f * stride;
                         uint8_t* d0 = c->h_color[cb] + (size_t)f * fbytes;
                         if (pitch == row) memcpy(d0, s0, fbytes);
-                        else for (int y = 0; y < c->pre_H; ++y) memcpy(d0 + (size_t)y * row, s0 + (size_t)y * pitch, row);
+                        else for (int y = 0; y < pp.H; ++y) memcpy(d0 + (size_t)y * row, s0 + (size_t)y * pitch, row);
                     }
                     CK(c, cudaMemcpyAsync(c->d_color[cb], c->h_color[cb], (size_t)m * fbytes, cudaMemcpyHostToDevice, c->s_copy));
                 } else if (pitch == row && stride == fbytes) {
@@ -1496,45 +1522,51 @@ int ffb_bracket_push_bgr(ffb_ctx* c, const uint8_t* bgr, int n, size_t pitch, si
                 } else {
                     for (int f = 0; f < m; ++f)
                         CK(c, cudaMemcpy2DAsync(c->d_color[cb] + (size_t)f * fbytes, row, src + (size_t)f * stride, pitch, row,
-                                                c->pre_H, cudaMemcpyHostToDevice, c->s_copy));
+                                                pp.H, cudaMemcpyHostToDevice, c->s_copy));
                 }
                 CK(c, cudaEventRecord(c->ev_ch2d[cb], c->s_copy));
                 CK(c, cudaStreamWaitEvent(c->s_comp, c->ev_ch2d[cb], 0));
                 dsrc = c->d_color[cb];
                 dstride = fbytes;
                 dpitch = (int)row;
-                TRY(launch_preprocess(c, dsrc, dstride, dpitch, c->d_u8[b] + (size_t)j * PRE_OUT * PRE_OUT, (size_t)PRE_OUT * PRE_OUT,
-                                      PRE_OUT, c->pre_xt, c->pre_yt, c->pre_T, c->pre_vr, c->pre_W, c->pre_H, m));
+                TRY(launch_preprocess(c, dsrc, dstride, dpitch, c->d_u8[b] + (size_t)j * obytes, pp, c->pre_xt, c->pre_yt, m));
                 CK(c, cudaEventRecord(c->ev_pre[cb], c->s_comp));
             } else {
-                TRY(launch_preprocess(c, dsrc, dstride, dpitch, c->d_u8[b] + (size_t)j * PRE_OUT * PRE_OUT, (size_t)PRE_OUT * PRE_OUT,
-                                      PRE_OUT, c->pre_xt, c->pre_yt, c->pre_T, c->pre_vr, c->pre_W, c->pre_H, m));
+                TRY(launch_preprocess(c, dsrc, dstride, dpitch, c->d_u8[b] + (size_t)j * obytes, pp, c->pre_xt, c->pre_yt, m));
             }
         }
         // the gray frames now sit in the device staging buffer: continue as for device input
-        TRY(process_batch(c, c->d_u8[b], nb, PRE_OUT, (size_t)PRE_OUT * PRE_OUT, PTR_DEVICE));
+        TRY(process_batch(c, c->d_u8[b], nb, pp.OW, obytes, PTR_DEVICE));
         i += nb;
     }
     return FFB_OK;
 }
 
-int ffb_stage_preprocess(ffb_ctx* c, const uint8_t* bgr, int W, int H, size_t pitch, int vr, uint8_t* gray) {
-    if (!c || !bgr || !gray || W < 2 || H < 2) return FFB_E_INVALID;
+static int stage_preprocess_plan(ffb_ctx* c, const uint8_t* bgr, size_t pitch, const ffb_ctx::PrePlan& p, uint8_t* gray) {
+    if (!c || !bgr || !gray || !plan_ok(p) || pitch < (size_t)p.W * 3) return fail(c, FFB_E_INVALID, "ffb_stage_preprocess: bad arguments");
     CK(c, cudaSetDevice(c->device));
-    const int T = vr ? 2 * PRE_OUT : PRE_OUT;
     Scratch s;
     uint8_t *d_src, *d_dst;
     int *dxt, *dyt;
-    const std::vector<int> xt = make_u8_resize_table(T, W, true), yt = make_u8_resize_table(T, H, false);
-    TRY(s.alloc(c, &d_src, (size_t)W * H * 3));
-    CK(c, cudaMemcpy2D(d_src, (size_t)W * 3, bgr, pitch, (size_t)W * 3, H, cudaMemcpyHostToDevice));
-    TRY(s.alloc(c, &d_dst, (size_t)PRE_OUT * PRE_OUT));
+    const std::vector<int> xt = make_u8_resize_table(p.TW, p.W, true), yt = make_u8_resize_table(p.TH, p.H, false);
+    TRY(s.alloc(c, &d_src, (size_t)p.W * p.H * 3));
+    CK(c, cudaMemcpy2D(d_src, (size_t)p.W * 3, bgr, pitch, (size_t)p.W * 3, p.H, cudaMemcpyHostToDevice));
+    TRY(s.alloc(c, &d_dst, (size_t)p.OW * p.OH));
     TRY(s.upload(c, &dxt, xt.data(), xt.size()));
     TRY(s.upload(c, &dyt, yt.data(), yt.size()));
-    TRY(launch_preprocess(c, d_src, (size_t)W * H * 3, W * 3, d_dst, (size_t)PRE_OUT * PRE_OUT, PRE_OUT, dxt, dyt, T, vr, W, H, 1));
+    TRY(launch_preprocess(c, d_src, (size_t)p.W * p.H * 3, p.W * 3, d_dst, p, dxt, dyt, 1));
     CK(c, cudaStreamSynchronize(c->s_comp));
-    CK(c, cudaMemcpy(gray, d_dst, (size_t)PRE_OUT * PRE_OUT, cudaMemcpyDeviceToHost));
+    CK(c, cudaMemcpy(gray, d_dst, (size_t)p.OW * p.OH, cudaMemcpyDeviceToHost));
     return FFB_OK;
+}
+int ffb_stage_preprocess(ffb_ctx* c, const uint8_t* bgr, int W, int H, size_t pitch, int vr, uint8_t* gray) {
+    return stage_preprocess_plan(c, bgr, pitch, reference_plan(W, H, vr), gray);
+}
+int ffb_stage_preprocess_window(ffb_ctx* c, const uint8_t* bgr, int W, int H, size_t pitch, int target_w, int target_h, int win_x,
+                                int win_y, int win_w, int win_h, uint8_t* gray) {
+    ffb_ctx::PrePlan p;
+    p.W = W; p.H = H; p.TW = target_w; p.TH = target_h; p.x0 = win_x; p.y0 = win_y; p.OW = win_w; p.OH = win_h;
+    return stage_preprocess_plan(c, bgr, pitch, p, gray);
 }
 
 // ---- instrumentation ---------------------------------------------------------------------

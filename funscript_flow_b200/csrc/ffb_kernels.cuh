@@ -134,7 +134,12 @@ __global__ void __launch_bounds__(TW* TH) k_pyramid_level(FfbPyrArgs a) {
 // the same order, as k_pyramid_level (the two paths agree to FMA-contraction rounding, <= 2 ulp).
 constexpr int PYR2_TX = 128, PYR2_TY = 32, PYR2_HL = 8;
 constexpr int PYR2_RW = PYR2_TX + 2 * PYR2_HL, PYR2_RH = PYR2_TY + 2 * PYR2_HL;
-constexpr size_t PYR2_SMEM = sizeof(float) * (PYR2_RW * PYR2_RH + PYR2_RH * PYR2_TX);
+// Shared-memory pitches are chosen for the 16-byte loads of the row passes: a quarter-warp (the unit a
+// 128-bit shared access is served in) reads chunks that are 32 or 64 bytes apart, so it is spread
+// over 2 or 4 window rows, and 148 = 20 (mod 32) puts those rows on disjoint banks.
+constexpr int PYR2_RWP = PYR2_RW + 4;
+constexpr int PYR2_PMAX = 80;                           // largest pitch of the row-pass result (level 1)
+constexpr size_t PYR2_SMEM = sizeof(float) * (PYR2_RWP * PYR2_RH + PYR2_RH * PYR2_PMAX);
 
 struct FfbPyr2Args {
     const uint8_t* src; size_t src_frame_stride; int src_pitch; int W, H;
@@ -159,19 +164,50 @@ __device__ __forceinline__ float ffb_blur_col_t(const float* col, int pitch, con
     return s;
 }
 
-template <int K, int R>
+// Per-level shape of the row pass: one task = NOUT adjacent outputs of one window row, computed from
+// NF4 aligned 16-byte loads held in registers; a quarter-warp covers 2^JB tasks along the row times
+// 2^RB rows; PP = pitch of the row-pass result (padded so its vector stores do not collide either).
+template <int K> struct FfbPyr2Shape;
+template <> struct FfbPyr2Shape<1> { static constexpr int R = 1, NOUT = 4, NF4 = 4, JB = 2, RB = 1, PP = 80; };
+template <> struct FfbPyr2Shape<2> { static constexpr int R = 4, NOUT = 2, NF4 = 4, JB = 2, RB = 1, PP = 48; };
+template <> struct FfbPyr2Shape<3> { static constexpr int R = 9, NOUT = 2, NF4 = 8, JB = 1, RB = 2, PP = 24; };
+
+template <int K>
 __device__ __forceinline__ void ffb_pyr2_level(const FfbPyr2Args& a, const float* reg, float* P, int X0, int Y0, int f,
                                                int tid) {
-    constexpr int OW = PYR2_TX >> K, OH = PYR2_TY >> K;
-    constexpr int OFF = K == 0 ? 0 : (1 << (K - 1)) - 1;     // first bilinear tap inside a 2^K cell
+    using SH = FfbPyr2Shape<K>;
+    constexpr int R = SH::R, NOUT = SH::NOUT, NF4 = SH::NF4, JB = SH::JB, RB = SH::RB, PP = SH::PP;
+    constexpr int S = 1 << K, OW = PYR2_TX >> K, OH = PYR2_TY >> K, NJ = OW / NOUT;
+    constexpr int OFF = (1 << (K - 1)) - 1;                 // first bilinear tap inside a 2^K cell
+    constexpr int BASE0 = (OFF + PYR2_HL - R) & ~3;          // aligned start of the first task's footprint
+    constexpr int C0 = OFF + PYR2_HL - BASE0;                // register index of output 0's first tap centre
+    static_assert(C0 - R >= 0 && C0 + (NOUT - 1) * S + 1 + R < 4 * NF4, "row-pass footprint");
+    static_assert(BASE0 + (NJ - 1) * NOUT * S + 4 * NF4 <= PYR2_RWP, "row-pass footprint leaves the window");
+    static_assert(PYR2_RH % (1 << RB) == 0 && NJ % (1 << JB) == 0 && PP >= OW && PP <= PYR2_PMAX, "task shape");
     const FfbTaps& t = a.taps[K];
     // pass 1: rows of the window -> P[ry][ox]
-    for (int i = tid; i < PYR2_RH * OW; i += 256) {
-        const int ry = i / OW, ox = i - ry * OW;
-        const float* row = reg + ry * PYR2_RW + (ox << K) + OFF + PYR2_HL;
-        float v = ffb_blur_row_t<R>(row, t);
-        if (K > 0) v = v * (1.f - 0.5f) + ffb_blur_row_t<R>(row + 1, t) * 0.5f;
-        P[ry * OW + ox] = v;
+    for (int i = tid; i < PYR2_RH * NJ; i += 256) {
+        const int jl = i & ((1 << JB) - 1), rl = (i >> JB) & ((1 << RB) - 1), rest = i >> (JB + RB);
+        const int rh = rest / (NJ >> JB), jh = rest - rh * (NJ >> JB);
+        const int j = (jh << JB) | jl, ry = (rh << RB) | rl;
+        float w[4 * NF4];
+        const float4* src4 = reinterpret_cast<const float4*>(reg + ry * PYR2_RWP + j * (NOUT * S) + BASE0);
+#pragma unroll
+        for (int q = 0; q < NF4; ++q) {
+            const float4 v = src4[q];
+            w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+        }
+        float o[NOUT];
+#pragma unroll
+        for (int n = 0; n < NOUT; ++n) {
+            const float* row = w + C0 + n * S;
+            float v = ffb_blur_row_t<R>(row, t);
+            v = v * (1.f - 0.5f) + ffb_blur_row_t<R>(row + 1, t) * 0.5f;
+            o[n] = v;
+        }
+        float* d = P + ry * PP + j * NOUT;
+        if (NOUT == 4) *reinterpret_cast<float4*>(d) = make_float4(o[0], o[1], o[NOUT > 2 ? 2 : 0], o[NOUT > 3 ? 3 : 0]);
+        else *reinterpret_cast<float2*>(d) = make_float2(o[0], o[1]);
     }
     __syncthreads();
     // pass 2
@@ -181,29 +217,29 @@ __device__ __forceinline__ void ffb_pyr2_level(const FfbPyr2Args& a, const float
         const int oy = i / OW, ox = i - oy * OW;
         const int x = (X0 >> K) + ox, y = (Y0 >> K) + oy;
         if (x < wk && y < hk) {
-            const float* col = P + ((oy << K) + OFF + PYR2_HL) * OW + ox;
-            float v = ffb_blur_col_t<R>(col, OW, t);
-            if (K > 0) v = v * (1.f - 0.5f) + ffb_blur_col_t<R>(col + OW, OW, t) * 0.5f;
+            const float* col = P + ((oy << K) + OFF + PYR2_HL) * PP + ox;
+            float v = ffb_blur_col_t<R>(col, PP, t);
+            v = v * (1.f - 0.5f) + ffb_blur_col_t<R>(col + PP, PP, t) * 0.5f;
             dst[(size_t)y * a.dp[K] + x] = v;
         }
     }
     __syncthreads();
 }
 
-// Level 0 (3 x 3 taps, no decimation) straight from the staged window: one task = 4 adjacent outputs
-// of a row from nine 16-byte shared loads, both passes in registers, one 16-byte store.  Same
-// expressions as ffb_blur_row_t<1> / ffb_blur_col_t<1>.
+// Level 0 (3 x 3 taps, no decimation) straight from the staged window: one task = a 4 x 4 block of
+// outputs from eighteen 16-byte shared loads (six window rows), both passes in registers, four 16-byte
+// stores.  Same expressions as ffb_blur_row_t<1> / ffb_blur_col_t<1>.
 __device__ __forceinline__ void ffb_pyr2_level0(const FfbPyr2Args& a, const float* reg, int X0, int Y0, int f, int tid) {
     const float k0 = a.taps[0].k[0], k1 = a.taps[0].k[1];
     float* dst = a.dst[0] + (size_t)f * a.dstride[0];
-    for (int t = tid; t < PYR2_TY * (PYR2_TX / 4); t += 256) {
-        const int oy = t / (PYR2_TX / 4), ox = 4 * (t - oy * (PYR2_TX / 4));
+    for (int t = tid; t < (PYR2_TY / 4) * (PYR2_TX / 4); t += 256) {
+        const int og = t / (PYR2_TX / 4), oy = 4 * og, ox = 4 * (t - og * (PYR2_TX / 4));
         const int x = X0 + ox, y = Y0 + oy;
         if (x >= a.W || y >= a.H) continue;
-        float hrow[3][4];
+        float hrow[6][4];
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            const float4* p = reinterpret_cast<const float4*>(reg + (oy + PYR2_HL - 1 + r) * PYR2_RW + ox + PYR2_HL - 4);
+        for (int r = 0; r < 6; ++r) {
+            const float4* p = reinterpret_cast<const float4*>(reg + (oy + PYR2_HL - 1 + r) * PYR2_RWP + ox + PYR2_HL - 4);
             const float4 q0 = p[0], q1 = p[1], q2 = p[2];          // window columns ox-4 .. ox+7
             const float v[6] = {q0.w, q1.x, q1.y, q1.z, q1.w, q2.x};   // columns ox-1 .. ox+4
 #pragma unroll
@@ -213,28 +249,32 @@ __device__ __forceinline__ void ffb_pyr2_level0(const FfbPyr2Args& a, const floa
                 hrow[r][j] = s;
             }
         }
-        float o[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float s = k0 * hrow[1][j];
-            s += k1 * (hrow[0][j] + hrow[2][j]);
-            o[j] = s;
-        }
-        float* d = dst + (size_t)y * a.dp[0] + x;
-        if (x + 3 < a.W) {
-            *reinterpret_cast<float4*>(d) = make_float4(o[0], o[1], o[2], o[3]);
-        } else {
+        for (int rr = 0; rr < 4; ++rr) {
+            if (y + rr >= a.H) break;
+            float o[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (x + j < a.W) d[j] = o[j];
+            for (int j = 0; j < 4; ++j) {
+                float s = k0 * hrow[rr + 1][j];
+                s += k1 * (hrow[rr][j] + hrow[rr + 2][j]);
+                o[j] = s;
+            }
+            float* d = dst + (size_t)(y + rr) * a.dp[0] + x;
+            if (x + 3 < a.W) {
+                *reinterpret_cast<float4*>(d) = make_float4(o[0], o[1], o[2], o[3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (x + j < a.W) d[j] = o[j];
+            }
         }
     }
 }
 
 __global__ void __launch_bounds__(256) k_pyramid_pow2(FfbPyr2Args a) {
     FFB_DYN_SMEM(float, smem);
-    float* reg = smem;                                  // [PYR2_RH][PYR2_RW]
-    float* P = smem + PYR2_RW * PYR2_RH;                // up to [PYR2_RH][PYR2_TX]
+    float* reg = smem;                                  // [PYR2_RH][PYR2_RWP]
+    float* P = smem + PYR2_RWP * PYR2_RH;               // [PYR2_RH][pitch of the level]
     const int tid = threadIdx.x;
     const int X0 = blockIdx.x * PYR2_TX, Y0 = blockIdx.y * PYR2_TY, f = blockIdx.z;
     const uint8_t* src = a.src + (size_t)f * a.src_frame_stride;
@@ -256,13 +296,14 @@ __global__ void __launch_bounds__(256) k_pyramid_pow2(FfbPyr2Args a) {
             int c2 = ffb_reflect1(min(sx + 2, n2), W), c3 = ffb_reflect1(min(sx + 3, n2), W);
             v = make_float4((float)__ldg(srow + c0), (float)__ldg(srow + c1), (float)__ldg(srow + c2), (float)__ldg(srow + c3));
         }
-        *reinterpret_cast<float4*>(reg + ry * PYR2_RW + 4 * wx) = v;
+        *reinterpret_cast<float4*>(reg + ry * PYR2_RWP + 4 * wx) = v;
     }
+    if (tid < PYR2_RH) *reinterpret_cast<float4*>(reg + tid * PYR2_RWP + PYR2_RW) = make_float4(0.f, 0.f, 0.f, 0.f);   // pitch padding
     __syncthreads();
     ffb_pyr2_level0(a, reg, X0, Y0, f, tid);
-    if (a.nlev > 1) ffb_pyr2_level<1, 1>(a, reg, P, X0, Y0, f, tid);
-    if (a.nlev > 2) ffb_pyr2_level<2, 4>(a, reg, P, X0, Y0, f, tid);
-    if (a.nlev > 3) ffb_pyr2_level<3, 9>(a, reg, P, X0, Y0, f, tid);
+    if (a.nlev > 1) ffb_pyr2_level<1>(a, reg, P, X0, Y0, f, tid);
+    if (a.nlev > 2) ffb_pyr2_level<2>(a, reg, P, X0, Y0, f, tid);
+    if (a.nlev > 3) ffb_pyr2_level<3>(a, reg, P, X0, Y0, f, tid);
 }
 
 // ======================================================================================
@@ -1045,19 +1086,20 @@ __global__ void __launch_bounds__(32) k_radial_finish(const double* partial, int
 // VR mode: the resize target is 512 x 512 and only its bottom-left 256 x 256 quadrant is produced.
 struct FfbPreArgs {
     const uint8_t* src; size_t src_frame_stride; int src_pitch;   // BGR, 3 bytes per pixel
-    uint8_t* dst; size_t dst_frame_stride; int dst_pitch;          // gray 256 x 256
+    uint8_t* dst; size_t dst_frame_stride; int dst_pitch;          // gray OW x OH
     const int* xt;    // [4][TW]: x0, x1, a0, a1 per resized column
     const int* yt;    // [4][TH]: y0, y1, b0, b1 per resized row
-    int TW, TH;       // resize target (256 x 256, or 512 x 512 in VR mode)
-    int y_off;        // first resized row that is kept (0, or 256 in VR mode)
+    int TW, TH;       // resize target (256 x 256, 512 x 512 in VR mode, or the source size)
+    int x_off, y_off; // first resized column / row that is kept (VR: the bottom-left quadrant)
+    int OW, OH;       // size of the kept window = size of the gray output
 };
 
 __global__ void __launch_bounds__(256) k_preprocess(FfbPreArgs a) {
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
     const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x >= 256 || y >= 256) return;
-    const int ry = y + a.y_off;
-    const int x0 = a.xt[x] * 3, x1 = a.xt[a.TW + x] * 3, a0 = a.xt[2 * a.TW + x], a1 = a.xt[3 * a.TW + x];
+    if (x >= a.OW || y >= a.OH) return;
+    const int ry = y + a.y_off, rx = x + a.x_off;
+    const int x0 = a.xt[rx] * 3, x1 = a.xt[a.TW + rx] * 3, a0 = a.xt[2 * a.TW + rx], a1 = a.xt[3 * a.TW + rx];
     const int y0 = a.yt[ry], y1 = a.yt[a.TH + ry], b0 = a.yt[2 * a.TH + ry], b1 = a.yt[3 * a.TH + ry];
     const uint8_t* src = a.src + (size_t)blockIdx.z * a.src_frame_stride;
     const uint8_t* r0 = src + (size_t)y0 * a.src_pitch;

@@ -100,6 +100,34 @@ def read_sampled_gray(video_path: str, indices: Sequence[int], params: Dict) -> 
     return out
 
 
+def preprocess_plan(src_w: int, src_h: int, params: Dict):
+    """(target, window, cut_scale) of the frame contract for `params`.
+
+    Reference modes: resize to 256x256 (F:1057) or, with `vr_mode`, to 512x512 and keep the bottom-left
+    quadrant (F:1076-1079).  Row N4 options the reference has no equivalent of:
+      native_resolution  no resampling: the flow runs on the decoded frame (VR: on the lower half of
+                         one eye of the side-by-side frame); `cut_threshold` (F:876, tuned for 256x256
+                         frames) is multiplied by cut_scale = sqrt(w*h)/256 because flow magnitudes
+                         are in pixels;
+      vr_eye             "left" (the reference's choice) or "right".
+    """
+    vr = bool(params.get("vr_mode"))
+    eye = str(params.get("vr_eye", "left")).lower()
+    if eye not in ("left", "right"):
+        raise ValueError("vr_eye must be 'left' or 'right'")
+    right = vr and eye == "right"
+    if params.get("native_resolution"):
+        if vr:
+            w, h = src_w // 2, src_h // 2
+            target, window = (src_w, src_h), (src_w - w if right else 0, src_h - h, w, h)
+        else:
+            target, window = (src_w, src_h), (0, 0, src_w, src_h)
+        return target, window, math.sqrt(window[2] * window[3]) / 256.0
+    if vr:
+        return (512, 512), (256 if right else 0, 256, 256, 256), 1.0
+    return (256, 256), (0, 0, 256, 256), 1.0
+
+
 def process_video_series(video_path: str, params: Dict, ctx=None, progress_callback=None, cancel_flag=None,
                          chunk_frames: int = 64):
     """Bracket loop over a video file with decode on the host and everything else on the GPU:
@@ -116,11 +144,15 @@ def process_video_series(video_path: str, params: Dict, ctx=None, progress_callb
     cap.release()
     if total < 2 or fps <= 0 or src_w < 2 or src_h < 2:
         raise IOError("unable to read video properties")
-    ctx.preprocess_configure(src_w, src_h, bool(params.get("vr_mode")))
+    target, window, cut_scale = preprocess_plan(src_w, src_h, params)
+    out_w, out_h = window[2], window[3]
+    ctx.preprocess_configure_window(src_w, src_h, target, window)
+    cut_threshold = float(params.get("cut_threshold", api.DEFAULT_CUT_THRESHOLD)) * cut_scale
     step = postproc.sampling_step(fps)
     indices = list(range(0, total, step))
     bracket = int(params.get("batch_size", 3000.0))
     batch = int(params.get("gpu_batch_frames", 64))
+    chunk_frames = max(1, min(chunk_frames, (256 << 20) // (src_w * src_h * 3)))   # bound the host-side stack
     values: List[float] = []
     cuts: List[bool] = []
     stamps: List[int] = []
@@ -135,8 +167,8 @@ def process_video_series(video_path: str, params: Dict, ctx=None, progress_callb
             for _ in range(nfr):
                 next(frames, None)
             continue
-        ctx.configure(256, 256, max(1, min(batch, nfr)), nfr - 1)
-        ctx.bracket_begin(bool(params.get("pov_mode", False)), float(params.get("cut_threshold", api.DEFAULT_CUT_THRESHOLD)))
+        ctx.configure(out_w, out_h, max(1, min(batch, nfr)), nfr - 1)
+        ctx.bracket_begin(bool(params.get("pov_mode", False)), cut_threshold)
         got = 0
         while got < nfr:
             chunk = []
@@ -212,9 +244,43 @@ def shard(items: Sequence, rank: int, world: int) -> List:
     return [it for i, it in enumerate(items) if i % world == rank]
 
 
+def video_cost(path: str) -> float:
+    """Work estimate of one video for the scheduler: its frame count (what the bracket loop iterates
+    over, F:1113, F:1145); the file size when the container cannot be read."""
+    try:
+        import cv2
+        cap = cv2.VideoCapture(path)
+        n = float(cap.get(cv2.CAP_PROP_FRAME_COUNT)) if cap.isOpened() else 0.0
+        cap.release()
+        if n > 0:
+            return n
+    except Exception:
+        pass
+    try:
+        return float(os.path.getsize(path)) * 1e-6
+    except OSError:
+        return 0.0
+
+
+def schedule_longest_first(items: Sequence, costs: Sequence[float], world: int) -> List[List]:
+    """Longest-processing-time-first assignment of whole videos to `world` GPUs: visit
+    the videos by decreasing cost and give each to the least-loaded rank.  Deterministic (ties: listing
+    order, then lowest rank), so every rank derives the same plan without communicating; each rank's
+    list keeps the listing order."""
+    order = sorted(range(len(items)), key=lambda i: (-float(costs[i]), i))
+    load = [0.0] * world
+    owner = [0] * len(items)
+    for i in order:
+        r = min(range(world), key=lambda k: (load[k], k))
+        owner[i] = r
+        load[r] += float(costs[i])
+    return [[items[i] for i in range(len(items)) if owner[i] == r] for r in range(world)]
+
+
 def run_headless(input_path: str, settings: Dict, log_func: Optional[Callable[[str], None]] = None) -> int:
     """F:2606-2638: walk the folder, process every supported video, log to run.log and stdout.
-    Under torchrun (one process per GPU) each rank takes every world-th video and writes run.<rank>.log.
+    Under torchrun (one process per GPU) the videos are spread longest-first over the ranks
+    (schedule_longest_first) and each rank writes run.<rank>.log.
     Returns the number of videos that reported an error."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -226,7 +292,9 @@ def run_headless(input_path: str, settings: Dict, log_func: Optional[Callable[[s
             logf.write(msg + "\n")
             logf.flush()
             print(msg)
-    vids = shard(list_videos(input_path), rank, world)
+    vids = list_videos(input_path)
+    if world > 1:
+        vids = schedule_longest_first(vids, [video_cost(v) for v in vids], world)[rank]
     if not vids:
         log_func("No video files found.")
     else:

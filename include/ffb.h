@@ -135,6 +135,19 @@ int  ffb_bracket_push_bgr(ffb_ctx* ctx, const uint8_t* bgr, int n_frames, size_t
 int  ffb_stage_preprocess(ffb_ctx* ctx, const uint8_t* bgr, int width, int height, size_t pitch, int vr_mode,
                           uint8_t* gray_256x256);
 
+/* Row N4: the same arithmetic with the geometry opened up.  The frame is resized to
+ * target_w x target_h (equal to the source size = no resampling: cv2.resize returns the frame
+ * unchanged and so does the fixed-point formula with weights 2048/0), the window
+ * [win_y, win_y+win_h) x [win_x, win_x+win_w) of the resized frame is kept and converted to gray;
+ * the context must then be configured for win_w x win_h frames.  The reference's two modes are
+ * (256,256, 0,0,256,256) (F:1057) and (512,512, 0,256,256,256) (F:1076-1079); native-resolution
+ * processing is (W,H, 0,0,W,H); one eye's lower half of a side-by-side VR frame at native resolution is
+ * (W,H, 0 or W/2, H/2, W/2, H/2). */
+int  ffb_preprocess_configure_window(ffb_ctx* ctx, int src_width, int src_height, int target_w, int target_h,
+                                     int win_x, int win_y, int win_w, int win_h);
+int  ffb_stage_preprocess_window(ffb_ctx* ctx, const uint8_t* bgr, int width, int height, size_t pitch,
+                                 int target_w, int target_h, int win_x, int win_y, int win_w, int win_h, uint8_t* gray);
+
 /* ---- instrumentation ----------------------------------------------------------------------
  * Kernel ids for ffb_kernel_stats. */
 #define FFB_K_PYRAMID   0

@@ -67,3 +67,12 @@ def frame_to_gray(bgr: np.ndarray, vr_mode: bool = False) -> np.ndarray:
     if vr_mode:
         return rgb_to_gray(resize_u8_linear(rgb, VR_SIZE, VR_SIZE)[VR_SIZE // 2:, :VR_SIZE // 2])
     return rgb_to_gray(resize_u8_linear(rgb, OUT, OUT))
+
+
+def frame_window_to_gray(bgr: np.ndarray, target, window) -> np.ndarray:
+    """Row N4 generalisation: cv2.resize(rgb, target)[y:y+h, x:x+w] -> gray, with target=(w, h) and
+    window=(x, y, w, h).  frame_to_gray is target=(256,256), window=(0,0,256,256) and, in VR mode,
+    target=(512,512), window=(0,256,256,256)."""
+    x, y, w, h = window
+    rgb = resize_u8_linear(np.ascontiguousarray(bgr[..., ::-1]), int(target[0]), int(target[1]))
+    return rgb_to_gray(rgb[y:y + h, x:x + w])

@@ -246,6 +246,52 @@ def check_preprocess(ctx, sizes=((360, 640), (300, 200), (256, 256))):
             assert np.array_equal(ctx.stage_preprocess(img, vr), pp.frame_to_gray(img, vr)), (h, w, vr)
 
 
+WINDOW_PLANS = (   # (src h, src w, target (w, h), window (x, y, w, h))
+    (120, 160, (160, 120), (0, 0, 160, 120)),        # native resolution: no resampling
+    (120, 160, (160, 120), (0, 60, 80, 60)),         # native VR, left eye, lower half
+    (120, 160, (160, 120), (80, 60, 80, 60)),        # native VR, right eye
+    (200, 300, (512, 512), (256, 256, 256, 256)),    # reference VR geometry, right eye
+    (97, 131, (200, 90), (13, 7, 150, 70)),          # arbitrary target and window
+    (90, 70, (333, 77), (300, 0, 33, 77)),           # window touching the right edge, odd sizes
+)
+
+
+def check_preprocess_window(ctx, plans=WINDOW_PLANS):
+    """Row N4: the windowed pre-processing (any resize target, any kept window) is bit-exact with the
+    oracle; the identity target returns the plain gray conversion of the frame."""
+    from oracle import preproc_np as pp
+    rng = np.random.default_rng(5)
+    for (h, w, target, window) in plans:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        got = ctx.stage_preprocess_window(img, target, window)
+        assert np.array_equal(got, pp.frame_window_to_gray(img, target, window)), (h, w, target, window)
+        if target == (w, h):
+            x, y, ww, hh = window
+            assert np.array_equal(got, pp.rgb_to_gray(img[y:y + hh, x:x + ww, ::-1]))
+
+
+def check_native_resolution_bracket(ctx, width=160, height=120, n=6, vr=False, eye="left"):
+    """Colour frames pushed with a native-resolution plan give exactly the result of converting them on
+    the host (oracle arithmetic) and pushing the gray window."""
+    import cv2
+    from funscript_flow_b200 import runner
+    from oracle import preproc_np as pp
+    clip = make_clip(width, height, n, seed=8)
+    bgr = np.stack([cv2.cvtColor(f, cv2.COLOR_GRAY2BGR) for f in clip])
+    bgr[..., 2] = (bgr[..., 2].astype(int) * 2 // 3).astype(np.uint8)
+    target, window, cut_scale = runner.preprocess_plan(width, height, {"native_resolution": True, "vr_mode": vr, "vr_eye": eye})
+    assert target == (width, height) and abs(cut_scale - np.sqrt(window[2] * window[3]) / 256.0) < 1e-12
+    gray = np.stack([pp.frame_window_to_gray(f, target, window) for f in bgr])
+    ra = api.process_bracket(gray, {"cut_threshold": 7.0 * cut_scale}, ctx=ctx, batch_frames=3)
+    ctx.configure(window[2], window[3], 3, n - 1)
+    ctx.preprocess_configure_window(width, height, target, window)
+    ctx.bracket_begin(False, 7.0 * cut_scale)
+    ctx.bracket_push_bgr(bgr)
+    rb = ctx.bracket_finish()
+    for k in ("scalar", "cut", "cx", "cy", "val", "mean_mag"):
+        assert np.array_equal(ra[k], rb[k]), k
+
+
 def check_bgr_push_equals_gray_push(ctx, width=320, height=200, n=7):
     """The fused upload path (colour frames -> device pre-processing -> hot path) gives exactly the
     result of pre-processing on the host and pushing gray frames."""

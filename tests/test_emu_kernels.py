@@ -58,6 +58,28 @@ def test_preprocess(emu_ctx):
     pc.check_bgr_push_equals_gray_push(emu_ctx)
 
 
+def test_preprocess_window_and_native_resolution(emu_ctx):
+    """Row N4: windowed pre-processing and brackets at the decoded resolution (plain and VR eyes)."""
+    pc.check_preprocess_window(emu_ctx)
+    pc.check_native_resolution_bracket(emu_ctx, 96, 64, 4)
+    pc.check_native_resolution_bracket(emu_ctx, 160, 128, 4, vr=True, eye="right")
+    # configuring the flow for another size than the window is refused, with the expected size in the text
+    emu_ctx.preprocess_configure_window(96, 64, (96, 64), (0, 0, 96, 64))
+    emu_ctx.configure(256, 256, 2, 4)
+    emu_ctx.bracket_begin(False, 7.0)
+    with pytest.raises(Exception, match="96x64"):
+        emu_ctx.bracket_push_bgr(np.zeros((2, 64, 96, 3), np.uint8))
+    emu_ctx.bracket_finish()
+    with pytest.raises(Exception):
+        emu_ctx.preprocess_configure_window(96, 64, (96, 64), (50, 0, 96, 64))    # window leaves the target
+    with pytest.raises(ValueError):
+        runner.preprocess_plan(96, 64, {"vr_mode": True, "vr_eye": "both"})
+    assert runner.preprocess_plan(1920, 1080, {}) == ((256, 256), (0, 0, 256, 256), 1.0)
+    assert runner.preprocess_plan(1920, 1080, {"vr_mode": True}) == ((512, 512), (0, 256, 256, 256), 1.0)
+    assert runner.preprocess_plan(1920, 1080, {"vr_mode": True, "vr_eye": "right"})[1] == (256, 256, 256, 256)
+    assert runner.preprocess_plan(3840, 1920, {"vr_mode": True, "native_resolution": True})[:2] == ((3840, 1920), (0, 960, 1920, 960))
+
+
 def test_process_video_file(emu_ctx, tmp_path):
     """process_video() on a small lossless clip: decode on the host, resize / gray / flow / reductions in
     the kernels; equals the host pre-processing path and honours the skip-if-exists rule (F:1105-1109)."""
@@ -82,6 +104,10 @@ def test_process_video_file(emu_ctx, tmp_path):
     assert acts == ref and len(acts) == 8
     logs.clear()
     assert runner.process_video(path, dict(prm, overwrite=False), logs.append) is False and any("Skipping" in l for l in logs)
+    # row N4: the same file at its native 160x120 (FFV1 is lossless, so the decoded frames are the clip)
+    res = runner.process_video_series(path, dict(prm, native_resolution=True), ctx=emu_ctx)
+    direct = api.process_bracket(clip, {"cut_threshold": 7.0 * np.sqrt(160 * 120) / 256.0}, ctx=emu_ctx, batch_frames=4)
+    assert res[0] == direct["scalar"].tolist() and res[1] == direct["cut"].tolist()
 
 
 def test_headless_folder_sharded_over_ranks(emu_ctx, tmp_path, monkeypatch):

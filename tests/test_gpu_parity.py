@@ -195,6 +195,20 @@ def test_preprocess_bit_exact(gpu_ctx):
     pc.check_bgr_push_equals_gray_push(gpu_ctx, 1920, 1080, 40)
 
 
+@pytest.mark.gpu
+def test_preprocess_window_and_native_resolution(gpu_ctx):
+    """Row N4: windowed pre-processing bit-exact at real sizes (1080p native, 4K side-by-side VR eyes);
+    a native-resolution bracket fed as colour frames equals the host-converted gray bracket."""
+    pc.check_preprocess_window(gpu_ctx)
+    pc.check_preprocess_window(gpu_ctx, plans=((1080, 1920, (1920, 1080), (0, 0, 1920, 1080)),
+                                               (1920, 3840, (3840, 1920), (0, 960, 1920, 960)),
+                                               (1920, 3840, (3840, 1920), (1920, 960, 1920, 960)),
+                                               (2160, 3840, (1280, 720), (100, 50, 1000, 600))))
+    pc.check_native_resolution_bracket(gpu_ctx, 1920, 1080, 6)
+    pc.check_native_resolution_bracket(gpu_ctx, 1280, 640, 5, vr=True, eye="right")
+
+
+
 def test_process_video_matches_reference_funscript(gpu_ctx, golden_dir, tmp_path):
     """End to end on the C1-style clip: the .funscript written by our process_video() has the same
     keyframe timestamps as the one the reference's process_video() wrote (recorded in video_c1.json)."""

@@ -63,6 +63,23 @@ def test_video_sharding():
     assert distributed.my_brackets([(0, 5), (5, 10), (10, 15)], 1, 2) == [1]
 
 
+def test_longest_first_video_schedule():
+    """Row N3: whole videos go to the GPUs longest-first; every rank derives the same plan."""
+    from funscript_flow_b200 import runner
+    vids = list("abcdefgh")
+    costs = [30, 5, 5, 5, 20, 10, 5, 10]
+    plan = runner.schedule_longest_first(vids, costs, 3)
+    assert sorted(sum(plan, [])) == vids and all(p == sorted(p) for p in plan)       # a partition, listing order kept
+    load = [sum(costs[vids.index(v)] for v in p) for p in plan]
+    assert max(load) == 30 and plan[0] == ["a"]                                      # the long video gets a GPU to itself
+    rr = [sum(costs[i] for i in range(len(vids)) if i % 3 == r) for r in range(3)]   # round-robin for comparison
+    assert max(load) < max(rr)
+    assert runner.schedule_longest_first(vids, costs, 3) == plan                     # deterministic
+    assert runner.schedule_longest_first(vids, [1] * 8, 1) == [vids]
+    assert runner.schedule_longest_first([], [], 2) == [[], []]
+    assert runner.video_cost("/nonexistent/clip.mp4") == 0.0
+
+
 def test_cli_settings_match_reference_quirks():
     """F:2642-2664: same keys and defaults; the keyframe flag is inverted twice."""
     from funscript_flow_b200.__main__ import build_parser, settings_from_args
@@ -73,3 +90,6 @@ def test_cli_settings_match_reference_quirks():
     assert s["keyframe_reduction"] is False and not s["overwrite"] and not s["vr_mode"] and not s["pov_mode"]
     s = settings_from_args(build_parser().parse_args(["clip.mp4", "--disable_keyframe_reduction", "--vr_mode", "--overwrite"]))
     assert s["keyframe_reduction"] is True and s["vr_mode"] and s["overwrite"]
+    # extension keys (row N4) appear only when asked for
+    s = settings_from_args(build_parser().parse_args(["clip.mp4", "--native_resolution", "--vr_mode", "--vr_eye", "right"]))
+    assert s["native_resolution"] is True and s["vr_eye"] == "right"

@@ -126,3 +126,10 @@ def test_preprocess_oracle_bit_exact_vs_cv2():
         rgb = cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
         assert np.array_equal(cv2.cvtColor(cv2.resize(rgb, (256, 256)), cv2.COLOR_RGB2GRAY), pp.frame_to_gray(img, False))
         assert np.array_equal(cv2.cvtColor(cv2.resize(rgb, (512, 512))[256:, :256], cv2.COLOR_RGB2GRAY), pp.frame_to_gray(img, True))
+    # row N4: any target / window, including the identity target (cv2.resize returns the frame itself)
+    import parity_checks as pc
+    for (h, w, target, (x, y, ww, hh)) in pc.WINDOW_PLANS:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        rgb = cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
+        want = cv2.cvtColor(np.ascontiguousarray(cv2.resize(rgb, target)[y:y + hh, x:x + ww]), cv2.COLOR_RGB2GRAY)
+        assert np.array_equal(want, pp.frame_window_to_gray(img, target, (x, y, ww, hh))), (h, w, target)
