@@ -408,6 +408,9 @@ int launch_polyexp(ffb_ctx* c, const float* src, size_t src_stride, int sp, int 
     FfbPolyArgs a;
     a.src = src; a.src_frame_stride = src_stride; a.sp = sp; a.w = w; a.h = h;
     a.dst = dst; a.plane = plane; a.rp = rp; a.c = c->poly;
+    // the kernel stores two pixels (32 bytes) of the float4 image per instruction
+    if (rp % 4 != 0 || ((uintptr_t)dst.base | (uintptr_t)dst.stride) % 32 != 0)
+        return fail(c, FFB_E_INVALID, "expansion output is not 32-byte aligned (pitch %d, stride %zu)", rp, dst.stride);
     if (!c->attr_poly) {
         CK(c, cudaFuncSetAttribute(k_polyexp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POLY_SMEM));
         c->attr_poly = true;
@@ -522,6 +525,9 @@ int launch_flow_iter(ffb_ctx* c, FfbRing R, size_t plane, int rp, int w, int h, 
         bpp = 48.0 + 8.0 * ((double)up->wc * up->hc) / ((double)w * h);
     }
     const double bytes = (double)npairs * bpp * w * h;
+    // the kernel stores four flow vectors with one 32-byte instruction
+    if (fop % 4 != 0 || ((uintptr_t)fout.base | (uintptr_t)fout.stride) % 32 != 0)
+        return fail(c, FFB_E_INVALID, "flow output is not 32-byte aligned (pitch %d, stride %zu)", fop, fout.stride);
     const IterCfg k = iter_cfg();
     // Variants kept after the round-1 sweeps (profiles/r1_sweep*.txt); the third number of FFB_ITER_CFG
     // selects min blocks per SM, with 6 / 7 meaning "horizontal phase first" (/ 8 outputs per task).
@@ -776,8 +782,6 @@ int flow_pairs(ffb_ctx* c, int p0, int np) {
                                           last ? toRing : toB, L.fp, cnt);
                 }
                 c->launch_stream = c->s_comp;
-    c->aux_stream = c->s_comp;
-    if (const char* e = getenv("FFB_FLOW_STREAMS")) c->flow_streams = atoi(e);
                 TRY(rc);
             }
         }

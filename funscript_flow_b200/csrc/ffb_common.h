@@ -56,6 +56,36 @@ __device__ __forceinline__ void ffb_dsmem_store(float* local_addr, unsigned rank
 }
 #endif
 
+// ---- 256-bit global store (sm_100+, STG.E.ENL2.256): eight floats at a 32-byte aligned address.
+// A thread that owns 32 contiguous bytes fills a whole DRAM/L2 sector with one instruction instead of
+// half a sector with each of two 16-byte stores.
+#ifdef FFB_EMU
+static inline void ffb_store_f8(float* p, float4 lo, float4 hi) {
+    reinterpret_cast<float4*>(p)[0] = lo;
+    reinterpret_cast<float4*>(p)[1] = hi;
+}
+#else
+__device__ __forceinline__ void ffb_store_f8(float* p, float4 lo, float4 hi) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(lo.x), "f"(lo.y), "f"(lo.z),
+                 "f"(lo.w), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w)
+                 : "memory");
+}
+#endif
+
+// 256-bit read-only global load (LDG.E.ENL2.256.CONSTANT): eight floats from a 32-byte aligned address
+#ifdef FFB_EMU
+static inline void ffb_load_f8(const float* p, float4& lo, float4& hi) {
+    lo = reinterpret_cast<const float4*>(p)[0];
+    hi = reinterpret_cast<const float4*>(p)[1];
+}
+#else
+__device__ __forceinline__ void ffb_load_f8(const float* p, float4& lo, float4& hi) {
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
+                 : "l"(p));
+}
+#endif
+
 #define FFB_MAX_LEVELS 4
 #define FFB_POLY_N 5
 #define FFB_WIN 15

@@ -413,9 +413,11 @@ __global__ void __launch_bounds__(256) k_polyexp(FfbPolyArgs a) {
         const size_t pix = (size_t)y * a.rp + x;
         float4* dA = reinterpret_cast<float4*>(dst0) + pix;
         float* dB = dst0 + 4 * a.plane + pix;
-        if (x + 3 < w) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) dA[j] = make_float4(o[0][j], o[1][j], o[2][j], o[3][j]);
+        if (x + 3 < w) {   // x % 4 == 0 and rows are 64-byte aligned: the four pixels are two aligned 32-byte halves
+            ffb_store_f8(reinterpret_cast<float*>(dA), make_float4(o[0][0], o[1][0], o[2][0], o[3][0]),
+                         make_float4(o[0][1], o[1][1], o[2][1], o[3][1]));
+            ffb_store_f8(reinterpret_cast<float*>(dA + 2), make_float4(o[0][2], o[1][2], o[2][2], o[3][2]),
+                         make_float4(o[0][3], o[1][3], o[2][3], o[3][3]));
             *reinterpret_cast<float4*>(dB) = make_float4(o[4][0], o[4][1], o[4][2], o[4][3]);
         } else {
 #pragma unroll
@@ -809,9 +811,9 @@ __global__ void __launch_bounds__(NT, MINB) k_flow_iter(FfbIterArgs a) {
             o[j].y = (g22 * h1 - g12 * h2) * idet;
         }
         float2* dst = fout + (yo * a.fop + hx);
-        if (hx + 3 < w) {
-            reinterpret_cast<float4*>(dst)[0] = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
-            reinterpret_cast<float4*>(dst)[1] = make_float4(o[2].x, o[2].y, o[3].x, o[3].y);
+        if (hx + 3 < w) {   // hx % 4 == 0, flow rows and buffers are 32-byte aligned (checked by the launcher)
+            ffb_store_f8(reinterpret_cast<float*>(dst), make_float4(o[0].x, o[0].y, o[1].x, o[1].y),
+                         make_float4(o[2].x, o[2].y, o[3].x, o[3].y));
         } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
@@ -907,6 +909,9 @@ struct FfbDivArgs {
     double* psum;                       // [pairs][gridDim.x]
 };
 
+// One thread = 4 adjacent pixels of a row: the flow vectors of the row above, the row itself and the row
+// below arrive as three 32-byte loads (rows are 32-byte aligned, pitch % 4 == 0); the horizontal
+// neighbours of the group's end pixels come from the adjacent lanes (one scalar load at the warp ends).
 __global__ void __launch_bounds__(256) k_divmag(FfbDivArgs a) {
     __shared__ unsigned long long skey[8];
     __shared__ double ssum[8];
@@ -915,6 +920,7 @@ __global__ void __launch_bounds__(256) k_divmag(FfbDivArgs a) {
     const int w = a.w, h = a.h, fp = a.fp;
     const int ylo = blockIdx.x * a.rows_per_block, yhi = min(ylo + a.rows_per_block, h);
     const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const int lane = threadIdx.x & 31;
     unsigned long long best = 0ull;
     double msum = 0.0;
     for (int y = ylo + ty; y < yhi; y += 4) {
@@ -922,24 +928,51 @@ __global__ void __launch_bounds__(256) k_divmag(FfbDivArgs a) {
         const float2* up = F + (size_t)(y > 0 ? y - 1 : 0) * fp;
         const float2* dn = F + (size_t)(y < h - 1 ? y + 1 : h - 1) * fp;
         const float ysc = (y > 0 && y < h - 1) ? 0.5f : 1.f;
-        for (int x = tx; x < w; x += 64) {
-            const float2 c = __ldg(row + x);
-            const float ua = __ldg(up + x).x, ub = __ldg(dn + x).x;
-            const float vl = __ldg(row + (x > 0 ? x - 1 : 0)).y, vr = __ldg(row + (x < w - 1 ? x + 1 : w - 1)).y;
-            const float xsc = (x > 0 && x < w - 1) ? 0.5f : 1.f;
-            // np.gradient: (f[i+1]-f[i-1])/2 inside, one-sided first differences at the ends
-            const float gu = __fmul_rn(__fsub_rn(ub, ua), ysc);
-            const float gv = __fmul_rn(__fsub_rn(vr, vl), xsc);
-            const float dv = __fadd_rn(gu, gv);
-            const unsigned long long key = ((unsigned long long)__float_as_uint(fabsf(dv)) << 32) |
-                                           (unsigned long long)(0xFFFFFFFFu - (unsigned)(y * w + x));
-            best = key > best ? key : best;
-            msum += (double)sqrtf(__fmaf_rn(c.x, c.x, __fmul_rn(c.y, c.y)));
+        // the trip count is the same for all lanes of a warp (the shuffles below need the whole warp)
+        for (int xw = 4 * (tx - lane); xw < w; xw += 256) {
+            const int x = xw + 4 * lane;
+            const bool active = x < w;
+            float cxv[4], cyv[4], uav[4], ubv[4];
+            if (active) {
+                float4 lo, hi;
+                ffb_load_f8(reinterpret_cast<const float*>(row + x), lo, hi);
+                cxv[0] = lo.x; cyv[0] = lo.y; cxv[1] = lo.z; cyv[1] = lo.w; cxv[2] = hi.x; cyv[2] = hi.y; cxv[3] = hi.z; cyv[3] = hi.w;
+                ffb_load_f8(reinterpret_cast<const float*>(up + x), lo, hi);
+                uav[0] = lo.x; uav[1] = lo.z; uav[2] = hi.x; uav[3] = hi.z;
+                ffb_load_f8(reinterpret_cast<const float*>(dn + x), lo, hi);
+                ubv[0] = lo.x; ubv[1] = lo.z; ubv[2] = hi.x; ubv[3] = hi.z;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) cxv[j] = cyv[j] = uav[j] = ubv[j] = 0.f;
+            }
+            float lft = __shfl_up_sync(0xffffffffu, cyv[3], 1);       // v at x - 1
+            float rgt = __shfl_down_sync(0xffffffffu, cyv[0], 1);     // v at x + 4
+            if (active) {
+                if (lane == 0 && x > 0) lft = __ldg(row + (x - 1)).y;
+                if (lane == 31 && x + 4 < w) rgt = __ldg(row + (x + 4)).y;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int xj = x + j;
+                    if (xj < w) {
+                        // np.gradient: (f[i+1]-f[i-1])/2 inside, one-sided first differences at the ends
+                        const float vl = xj > 0 ? (j > 0 ? cyv[j > 0 ? j - 1 : 0] : lft) : cyv[0];
+                        const float vr = xj < w - 1 ? (j < 3 ? cyv[j < 3 ? j + 1 : 3] : rgt) : cyv[j];
+                        const float xsc = (xj > 0 && xj < w - 1) ? 0.5f : 1.f;
+                        const float gu = __fmul_rn(__fsub_rn(ubv[j], uav[j]), ysc);
+                        const float gv = __fmul_rn(__fsub_rn(vr, vl), xsc);
+                        const float dv = __fadd_rn(gu, gv);
+                        const unsigned long long key = ((unsigned long long)__float_as_uint(fabsf(dv)) << 32) |
+                                                       (unsigned long long)(0xFFFFFFFFu - (unsigned)(y * w + xj));
+                        best = key > best ? key : best;
+                        msum += (double)sqrtf(__fmaf_rn(cxv[j], cxv[j], __fmul_rn(cyv[j], cyv[j])));
+                    }
+                }
+            }
         }
     }
     best = ffb_warp_max_u64(best);
     msum = ffb_warp_sum(msum);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
     if (lane == 0) { skey[warp] = best; ssum[warp] = msum; }
     __syncthreads();
     if (threadIdx.x == 0) {
