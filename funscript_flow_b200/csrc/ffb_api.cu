@@ -197,6 +197,10 @@ struct ffb_ctx {
     Level lev[FFB_MAX_LEVELS];
     float* R = nullptr;
     size_t r_slot_floats = 0;
+    // texture views of the expansion ring (one float4 view + one float view per element), see TX in k_flow_iter
+    std::vector<cudaTextureObject_t> h_tex4, h_tex1;
+    cudaTextureObject_t *d_tex4 = nullptr, *d_tex1 = nullptr;
+    int iter_tex = 0;      // TX variant used by the bracket path (0 = LSU loads only)
     float2* ring = nullptr;
     size_t ring_stride = 0;   // float2 per ring element
     uint8_t* d_u8[2] = {nullptr, nullptr};
@@ -440,6 +444,9 @@ int launch_upsample(ffb_ctx* c, const float2* src, size_t src_stride, int sp, in
 
 // Tunables of the fused iteration kernel (threads per CTA x rows per step, rows per segment).
 // Defaults are compiled in; FFB_ITER_CFG=NTxU and FFB_ITER_SH=rows override them for tuning runs.
+#ifndef FFB_ITER_TEX_DEFAULT
+#define FFB_ITER_TEX_DEFAULT 0
+#endif
 struct IterCfg { int nt, u, minb, sh; };
 IterCfg iter_cfg() {
     static IterCfg cfg = [] {
@@ -455,7 +462,62 @@ IterCfg iter_cfg() {
     return cfg;
 }
 
-template <int NT, int U, int MINB, bool HFIRST = false, int HO = 4, bool CL = false>
+// Linear-memory texture object over `bytes` at `ptr` with float4 or float texels.
+int make_linear_texture(ffb_ctx* c, const void* ptr, size_t bytes, bool vec4, cudaTextureObject_t* out) {
+#ifdef FFB_EMU
+    (void)c; (void)bytes; (void)vec4;
+    *out = (cudaTextureObject_t)(uintptr_t)ptr;      // tests/emu: tex1Dfetch indexes the pointer
+#else
+    cudaResourceDesc rd = {};
+    cudaTextureDesc td = {};
+    rd.resType = cudaResourceTypeLinear;
+    rd.res.linear.devPtr = const_cast<void*>(ptr);
+    rd.res.linear.desc = vec4 ? cudaCreateChannelDesc<float4>() : cudaCreateChannelDesc<float>();
+    rd.res.linear.sizeInBytes = bytes;
+    td.readMode = cudaReadModeElementType;
+    td.filterMode = cudaFilterModePoint;
+    td.addressMode[0] = cudaAddressModeClamp;
+    td.normalizedCoords = 0;
+    CK(c, cudaCreateTextureObject(out, &rd, &td, nullptr));
+#endif
+    return FFB_OK;
+}
+
+void free_textures(ffb_ctx* c) {
+    for (cudaTextureObject_t t : c->h_tex4) cudaDestroyTextureObject(t);
+    for (cudaTextureObject_t t : c->h_tex1) cudaDestroyTextureObject(t);
+    c->h_tex4.clear(); c->h_tex1.clear();
+    dev_free(c->d_tex4); dev_free(c->d_tex1);
+    c->iter_tex = 0;
+}
+
+// Texture views of the S elements of the expansion ring.  Skipped (LSU loads only) when an element
+// exceeds the device's linear-texture width.
+int make_ring_textures(ffb_ctx* c) {
+    free_textures(c);
+    static const int want = getenv("FFB_ITER_TEX") ? atoi(getenv("FFB_ITER_TEX")) : FFB_ITER_TEX_DEFAULT;
+    if (want <= 0 || want > 4) return FFB_OK;
+    size_t max_texels = (size_t)1 << 27;
+#ifndef FFB_EMU
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxTexture1DLinearWidth, c->device) == cudaSuccess && v > 0) max_texels = (size_t)v;
+#endif
+    if (c->r_slot_floats > max_texels) return FFB_OK;
+    for (int s = 0; s < c->S; ++s) {
+        cudaTextureObject_t t4 = 0, t1 = 0;
+        const float* base = c->R + (size_t)s * c->r_slot_floats;
+        TRY(make_linear_texture(c, base, c->r_slot_floats * sizeof(float), true, &t4));
+        c->h_tex4.push_back(t4);
+        TRY(make_linear_texture(c, base, c->r_slot_floats * sizeof(float), false, &t1));
+        c->h_tex1.push_back(t1);
+    }
+    TRY(upload_vec(c, &c->d_tex4, c->h_tex4));
+    TRY(upload_vec(c, &c->d_tex1, c->h_tex1));
+    c->iter_tex = want;
+    return FFB_OK;
+}
+
+template <int NT, int U, int MINB, bool HFIRST = false, int HO = 4, bool CL = false, int TX = 0>
 int launch_flow_iter_t(ffb_ctx* c, FfbIterArgs a, int npairs, int sh_target, double bytes) {
     const int w = a.w, h = a.h;
     int gx;
@@ -468,7 +530,7 @@ int launch_flow_iter_t(ffb_ctx* c, FfbIterArgs a, int npairs, int sh_target, dou
         gx = 2 * nclusters;
         // the row buffer holds NT + 16 positions: the seam offset NT - SW must stay within 16 columns;
         // widths that do not split into such clusters use the plain kernel
-        if (a.SW < NT - 16) return launch_flow_iter_t<NT, U, MINB, HFIRST, HO, false>(c, a, npairs, sh_target, bytes);
+        if (a.SW < NT - 16) return launch_flow_iter_t<NT, U, MINB, HFIRST, HO, false, TX>(c, a, npairs, sh_target, bytes);
     } else {
         const int sw_max = (NT - 2 * FFB_WIN_R) / HO * HO;
         const int nstrips = (w + sw_max - 1) / sw_max;
@@ -487,7 +549,7 @@ int launch_flow_iter_t(ffb_ctx* c, FfbIterArgs a, int npairs, int sh_target, dou
     if (nseg < 1) nseg = 1;
     a.SH = (h + nseg - 1) / nseg;
     const int gy = (h + a.SH - 1) / a.SH;
-    auto kfn = a.up_src ? k_flow_iter<NT, U, MINB, HFIRST, true, HO, CL> : k_flow_iter<NT, U, MINB, HFIRST, false, HO, CL>;
+    auto kfn = a.up_src ? k_flow_iter<NT, U, MINB, HFIRST, true, HO, CL, TX> : k_flow_iter<NT, U, MINB, HFIRST, false, HO, CL, TX>;
     const size_t smem = ffb_flow_iter_smem<NT, U, CL>();
     if (!c->attr_iter.count((const void*)kfn)) {
         CK(c, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -511,10 +573,15 @@ struct UpSrc {   // coarser-level flow to be up-sampled inside the iteration ker
     const float2* src = nullptr; size_t stride = 0; int sp = 0, wc = 0, hc = 0;
 };
 
+// tex_off >= 0: R is the context's expansion ring and tex_off the float offset of the level inside a ring
+// element, so the texture views may be used; -1 (stage hooks on scratch buffers): LSU loads only.
 int launch_flow_iter(ffb_ctx* c, FfbRing R, size_t plane, int rp, int w, int h, const float2* fin, size_t fin_stride,
-                     int fip, FfbRing fout, int fop, int npairs, const UpSrc* up = nullptr) {
+                     int fip, FfbRing fout, int fop, int npairs, const UpSrc* up = nullptr, long long tex_off = -1) {
     FfbIterArgs a;
     a.R = R; a.plane = (int)plane; a.rp = rp; a.w = w; a.h = h;
+    a.tex4 = c->d_tex4; a.tex1 = c->d_tex1; a.texA = a.texB = 0;
+    const int tx = (tex_off >= 0 && c->d_tex4) ? c->iter_tex : 0;
+    if (tx) { a.texA = (unsigned)(tex_off / 4); a.texB = (unsigned)(tex_off + 4 * (long long)plane); }
     a.fin = fin; a.fin_stride = fin_stride; a.fip = fip; a.fout = fout; a.fop = fop;
     a.SW = a.SH = 0;
     a.up_src = nullptr; a.up_stride = 0; a.usp = a.wc = a.hc = 0;
@@ -533,15 +600,19 @@ int launch_flow_iter(ffb_ctx* c, FfbRing R, size_t plane, int rp, int w, int h, 
     // selects min blocks per SM, with 6 / 7 meaning "horizontal phase first" (/ 8 outputs per task).
     const int key = k.nt * 100 + k.u * 10 + k.minb;
     switch (key) {
-        case 12823: return launch_flow_iter_t<128, 2, 3>(c, a, npairs, k.sh, bytes);             // gather first, 3 CTAs/SM
         case 12824: return launch_flow_iter_t<128, 2, 4>(c, a, npairs, k.sh, bytes);             // gather first, 4 CTAs/SM
         case 12827: return launch_flow_iter_t<128, 2, 4, true, 8>(c, a, npairs, k.sh, bytes);    // hfirst, 8 outputs / task
-        case 12846: return launch_flow_iter_t<128, 4, 3, true>(c, a, npairs, k.sh, bytes);       // 4 rows / step
-        case 12848: return launch_flow_iter_t<128, 4, 3, true, 4, true>(c, a, npairs, k.sh, bytes);   // clusters, 4 rows / step
         case 12828:   // "x8": hfirst + 2-CTA clusters sharing the seam columns through DSMEM
             return launch_flow_iter_t<128, 2, 4, true, 4, true>(c, a, npairs, k.sh, bytes);
-        case 25626: return launch_flow_iter_t<256, 2, 2, true>(c, a, npairs, k.sh, bytes);       // 256-thread strips
-        default:    return launch_flow_iter_t<128, 2, 4, true>(c, a, npairs, k.sh, bytes);       // 128x2, horizontal first
+        default: break;
+    }
+    // default: 128 threads x 2 rows per step, horizontal phase first; TX = loads moved to the texture pipe
+    switch (tx) {
+        case 1:  return launch_flow_iter_t<128, 2, 4, true, 4, false, 1>(c, a, npairs, k.sh, bytes);
+        case 2:  return launch_flow_iter_t<128, 2, 4, true, 4, false, 2>(c, a, npairs, k.sh, bytes);
+        case 3:  return launch_flow_iter_t<128, 2, 4, true, 4, false, 3>(c, a, npairs, k.sh, bytes);
+        case 4:  return launch_flow_iter_t<128, 2, 4, true, 4, false, 4>(c, a, npairs, k.sh, bytes);
+        default: return launch_flow_iter_t<128, 2, 4, true>(c, a, npairs, k.sh, bytes);
     }
 }
 
@@ -554,6 +625,7 @@ void free_geometry(ffb_ctx* c) {
         dev_free(L.I); dev_free(L.fA); dev_free(L.fB);
         L = Level();
     }
+    free_textures(c);
     dev_free(c->R); dev_free(c->ring);
     for (int b = 0; b < 2; ++b) {
         dev_free(c->d_u8[b]);
@@ -617,8 +689,9 @@ int configure(ffb_ctx* c, int W, int H, int B, int maxPairs) {
             TRY(dev_alloc(c, &L.fB, (size_t)B * L.fp * L.h));
         }
     }
-    c->r_slot_floats = off;
+    c->r_slot_floats = (off + 127) / 128 * 128;      // 512-byte multiples: texture views of the elements need it
     TRY(dev_alloc(c, &c->R, (size_t)c->S * c->r_slot_floats));
+    TRY(make_ring_textures(c));
     c->fp0 = c->lev[p.n - 1].fp;
     c->ring_stride = (size_t)c->fp0 * H;
     TRY(dev_alloc(c, &c->ring, (size_t)c->ring_n * c->ring_stride));
@@ -774,12 +847,13 @@ int flow_pairs(ffb_ctx* c, int p0, int np) {
                         up.src = C.fB + (size_t)off * up.stride; up.sp = C.fp; up.wc = C.w; up.hc = C.h;
                     }
                     rc = launch_flow_iter(c, R, L.plane, L.rp, L.w, L.h, fin0 ? fin0 + (size_t)off * fstride : nullptr, fstride,
-                                          L.fp, toB, L.fp, cnt, &up);
+                                          L.fp, toB, L.fp, cnt, &up, (long long)L.r_off);
                 } else if (it == 1) {
-                    rc = launch_flow_iter(c, R, L.plane, L.rp, L.w, L.h, L.fB + (size_t)off * fstride, fstride, L.fp, toA, L.fp, cnt);
+                    rc = launch_flow_iter(c, R, L.plane, L.rp, L.w, L.h, L.fB + (size_t)off * fstride, fstride, L.fp, toA, L.fp, cnt,
+                                          nullptr, (long long)L.r_off);
                 } else {
                     rc = launch_flow_iter(c, R, L.plane, L.rp, L.w, L.h, L.fA + (size_t)off * fstride, fstride, L.fp,
-                                          last ? toRing : toB, L.fp, cnt);
+                                          last ? toRing : toB, L.fp, cnt, nullptr, (long long)L.r_off);
                 }
                 c->launch_stream = c->s_comp;
                 TRY(rc);

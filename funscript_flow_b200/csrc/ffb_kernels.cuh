@@ -550,6 +550,10 @@ struct FfbIterArgs {
     // A1e fused (exact 2:1 levels only): when up_src != NULL the incoming flow is the coarser level's
     // result, up-sampled and doubled on the fly instead of being read from `fin`.
     const float2* up_src; size_t up_stride; int usp; int wc, hc;
+    // TX > 0: part of the R1 footprint is fetched through the texture pipe.  One float4 view and one
+    // float view (linear-memory texture objects) per element of the expansion ring `R`; texA / texB are
+    // the texel offsets of this level's float4 image / xy plane inside a ring element.
+    const cudaTextureObject_t* tex4; const cudaTextureObject_t* tex1; unsigned texA, texB;
 };
 
 template <int NT, int U, bool CL = false>
@@ -569,8 +573,14 @@ struct FfbGather {
 // Expansion layout (written by k_polyexp): per frame-level a float4 image A[h][rp] holding
 // (d/dy, d/dx, yy, xx) per pixel followed by a float plane B[h][rp] holding xy.  A 2x2 bilinear
 // footprint is then 4 x 16-byte + 4 x 4-byte loads off two row addresses instead of 20 scalar loads.
+// TX selects which loads of the R1 footprint go through the texture pipe instead of the LSU pipe (the
+// kernel is bound by LSU data-pipe wavefronts, shared + global; the texture pipe is otherwise idle):
+// 0 none, 1 the four xy scalars, 2 + the (y1+1, x1+1) vector, 4 + the whole y1+1 row, 3 everything.
+// Same addresses, same values: the result does not depend on TX.
+template <int TX>
 __device__ __forceinline__ void ffb_gather_issue(const float4* __restrict__ A0, const float* __restrict__ B0,
                                                  const float4* __restrict__ A1, const float* __restrict__ B1,
+                                                 cudaTextureObject_t T4, cudaTextureObject_t T1, unsigned texA, unsigned texB,
                                                  int rp, int w, int h, int x, int y, float2 d, FfbGather& g) {
     float fx = (float)x + d.x, fy = (float)y + d.y;
     const float x1f = floorf(fx), y1f = floorf(fy);
@@ -584,17 +594,27 @@ __device__ __forceinline__ void ffb_gather_issue(const float4* __restrict__ A0, 
     const unsigned o0 = (unsigned)(y * rp + x), o1 = (unsigned)(ys * rp + xs);
     const float4 q = __ldg(A0 + o0);
     const float q4 = __ldg(B0 + o0);
-    const float4 t00 = __ldg(A1 + o1), t01 = __ldg(A1 + o1 + 1);
-    const float4 t10 = __ldg(A1 + o1 + rp), t11 = __ldg(A1 + o1 + rp + 1);
+    const int ia = (int)(texA + o1), ib = (int)(texB + o1);
+    const float4 t00 = TX == 3 ? tex1Dfetch<float4>(T4, ia) : __ldg(A1 + o1);
+    const float4 t01 = TX == 3 ? tex1Dfetch<float4>(T4, ia + 1) : __ldg(A1 + o1 + 1);
+    const float4 t10 = TX >= 3 ? tex1Dfetch<float4>(T4, ia + rp) : __ldg(A1 + o1 + rp);
+    const float4 t11 = TX >= 2 ? tex1Dfetch<float4>(T4, ia + rp + 1) : __ldg(A1 + o1 + rp + 1);
     g.r0[0] = q.x; g.r0[1] = q.y; g.r0[2] = q.z; g.r0[3] = q.w; g.r0[4] = q4;
     g.t[0][0] = t00.x; g.t[0][1] = t01.x; g.t[0][2] = t10.x; g.t[0][3] = t11.x;
     g.t[1][0] = t00.y; g.t[1][1] = t01.y; g.t[1][2] = t10.y; g.t[1][3] = t11.y;
     g.t[2][0] = t00.z; g.t[2][1] = t01.z; g.t[2][2] = t10.z; g.t[2][3] = t11.z;
     g.t[3][0] = t00.w; g.t[3][1] = t01.w; g.t[3][2] = t10.w; g.t[3][3] = t11.w;
-    g.t[4][0] = __ldg(B1 + o1);
-    g.t[4][1] = __ldg(B1 + o1 + 1);
-    g.t[4][2] = __ldg(B1 + o1 + rp);
-    g.t[4][3] = __ldg(B1 + o1 + rp + 1);
+    if (TX >= 1) {
+        g.t[4][0] = tex1Dfetch<float>(T1, ib);
+        g.t[4][1] = tex1Dfetch<float>(T1, ib + 1);
+        g.t[4][2] = tex1Dfetch<float>(T1, ib + rp);
+        g.t[4][3] = tex1Dfetch<float>(T1, ib + rp + 1);
+    } else {
+        g.t[4][0] = __ldg(B1 + o1);
+        g.t[4][1] = __ldg(B1 + o1 + 1);
+        g.t[4][2] = __ldg(B1 + o1 + rp);
+        g.t[4][3] = __ldg(B1 + o1 + rp + 1);
+    }
 }
 
 __device__ __forceinline__ void ffb_gather_finish(const FfbGather& g, int w, int h, int x, int y, float m[5]) {
@@ -644,7 +664,7 @@ __device__ __forceinline__ void ffb_up2(int d, int src_n, int& i0, int& i1, floa
 // each CTA computes the vertical sums of its own NT columns only and the few columns next to the seam
 // are exchanged through distributed shared memory (each boundary thread also stores its sums into
 // the partner's row buffer), so the 14-column halo is paid once per cluster instead of once per CTA.
-template <int NT, int U, int MINB, bool HFIRST, bool UP2X, int HO, bool CL>
+template <int NT, int U, int MINB, bool HFIRST, bool UP2X, int HO, bool CL, int TX = 0>
 __global__ void __launch_bounds__(NT, MINB) k_flow_iter(FfbIterArgs a) {
     static_assert(HO == 4 || HO == 8, "outputs per horizontal task");
     constexpr int HP = CL ? NT + 16 : NT + 4;
@@ -660,6 +680,8 @@ __global__ void __launch_bounds__(NT, MINB) k_flow_iter(FfbIterArgs a) {
     const float4* A1 = reinterpret_cast<const float4*>(ffb_ring_at(a.R, pair + 1));
     const float* B0 = reinterpret_cast<const float*>(A0 + a.plane);
     const float* B1 = reinterpret_cast<const float*>(A1 + a.plane);
+    const int slot1 = (a.R.first + pair + 1) % a.R.mod;
+    const cudaTextureObject_t T4 = TX >= 2 ? a.tex4[slot1] : 0, T1 = TX >= 1 ? a.tex1[slot1] : 0;
     const float2* fin = a.fin ? a.fin + (size_t)pair * a.fin_stride : nullptr;
     float2* fout = reinterpret_cast<float2*>(ffb_ring_at(a.fout, pair));
     const int w = a.w, h = a.h;
@@ -861,7 +883,7 @@ __global__ void __launch_bounds__(NT, MINB) k_flow_iter(FfbIterArgs a) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int yc = ffb_clampi(y0 - FFB_WIN_R + s * U + u, 0, h - 1);
-            ffb_gather_issue(A0, B0, A1, B1, a.rp, w, h, xc, yc, d[u], g[u]);
+            ffb_gather_issue<TX>(A0, B0, A1, B1, T4, T1, a.texA, a.texB, a.rp, w, h, xc, yc, d[u], g[u]);
         }
         load_flow(s + 1, dn);
         // ---- while those are in flight: horizontal phase of the previous step

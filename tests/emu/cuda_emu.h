@@ -311,5 +311,9 @@ static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) {
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
+// linear-memory textures: the "object" is the device pointer itself (see ffb_make_linear_texture)
+typedef unsigned long long cudaTextureObject_t;
+template <class T> static inline T tex1Dfetch(cudaTextureObject_t t, int i) { return reinterpret_cast<const T*>(t)[i]; }
+static inline cudaError_t cudaDestroyTextureObject(cudaTextureObject_t) { return cudaSuccess; }
 static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void*) { a->type = cudaMemoryTypeUnregistered; a->device = 0; return cudaSuccess; }
 template <class K> static inline cudaError_t cudaFuncSetAttribute(K, int, int) { return cudaSuccess; }
