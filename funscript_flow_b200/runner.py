@@ -128,6 +128,12 @@ def preprocess_plan(src_w: int, src_h: int, params: Dict):
     return (256, 256), (0, 0, 256, 256), 1.0
 
 
+def default_batch_frames(width: int, height: int) -> int:
+    """Frames per GPU batch: 64 up to 4K, fewer above so that the per-batch device buffers (about
+    64 bytes per pixel and frame) stay near 35 GB at any frame size."""
+    return max(2, min(64, int(64 * (3840 * 2160) / max(1, width * height))))
+
+
 def process_video_series(video_path: str, params: Dict, ctx=None, progress_callback=None, cancel_flag=None,
                          chunk_frames: int = 64):
     """Bracket loop over a video file with decode on the host and everything else on the GPU:
@@ -151,7 +157,7 @@ def process_video_series(video_path: str, params: Dict, ctx=None, progress_callb
     step = postproc.sampling_step(fps)
     indices = list(range(0, total, step))
     bracket = int(params.get("batch_size", 3000.0))
-    batch = int(params.get("gpu_batch_frames", 64))
+    batch = int(params.get("gpu_batch_frames", default_batch_frames(out_w, out_h)))
     chunk_frames = max(1, min(chunk_frames, (256 << 20) // (src_w * src_h * 3)))   # bound the host-side stack
     values: List[float] = []
     cuts: List[bool] = []
