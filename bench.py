@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--batch-frames", type=int, default=64)
     ap.add_argument("--cpu-sample-pairs", type=int, default=0, help="0 = 2 x host cores (bounded to 8..64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the GPU's NUMA node")
     return ap.parse_args()
 
 
@@ -162,6 +163,12 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
+    # host side of the e2e path: staging buffers and upload calls on the NUMA node of the GPU's PCIe root
+    all_cpus = os.sched_getaffinity(0)
+    numa_node = None
+    if not args.no_numa_bind:
+        from funscript_flow_b200 import distributed as ffdist
+        numa_node = ffdist.bind_to_gpu_numa_node(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -262,7 +269,8 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"C2: synthetic {W}x{H} 30 fps clip, window of {nf} frames per step per GPU",
                        "pairs_per_step": P, "batch_frames": args.batch_frames, "levels": 4, "iterations": 3,
-                       "l2": "inputs_exceed_l2 (per-step working set >> 126 MB)", "parallelism": f"brackets x{world}"},
+                       "l2": "inputs_exceed_l2 (per-step working set >> 126 MB)", "parallelism": f"brackets x{world}",
+                       "numa_node": numa_node},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(nf * W * H), "d2h_bytes_per_step": int(P * 41),
                     "ms_per_step": 1000 * wall_e2e / args.steps},
             "gpu_launches": int(launches),
@@ -290,6 +298,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             from oracle import cpu_pipeline
             import cv2
+            os.sched_setaffinity(0, all_cpus)      # the CPU baseline gets every host core again
             cores = cpu_pipeline.usable_cores()
             sample = args.cpu_sample_pairs or int(min(64, max(8, 2 * cores)))
             sample = min(sample, P)

@@ -42,6 +42,7 @@ def load(path: Optional[str] = None) -> C.CDLL:
     sig = {
         "ffb_version": (i32, []),
         "ffb_device_count": (i32, [i32p]),
+        "ffb_device_pci_bus_id": (i32, [i32, C.c_char_p, i32]),
         "ffb_last_error": (C.c_char_p, [vp]),
         "ffb_create": (i32, [i32, C.POINTER(vp)]),
         "ffb_destroy": (None, [vp]),
@@ -91,6 +92,13 @@ def device_count(lib_path: Optional[str] = None) -> int:
     n = C.c_int32(0)
     load(lib_path).ffb_device_count(C.byref(n))
     return int(n.value)
+
+
+def device_pci_bus_id(device: int = 0, lib_path: Optional[str] = None) -> Optional[str]:
+    buf = C.create_string_buffer(32)
+    if load(lib_path).ffb_device_pci_bus_id(int(device), buf, 32) != 0:
+        return None
+    return buf.value.decode().lower()
 
 
 def level_plan(width: int, height: int, lib_path: Optional[str] = None):

@@ -1110,6 +1110,12 @@ int ffb_device_count(int* n) {
     return FFB_OK;
 }
 
+int ffb_device_pci_bus_id(int device, char* buf, int buf_len) {
+    if (!buf || buf_len < 16) return FFB_E_INVALID;
+    if (cudaDeviceGetPCIBusId(buf, buf_len, device) != cudaSuccess) { cudaGetLastError(); buf[0] = 0; return FFB_E_NODEVICE; }
+    return FFB_OK;
+}
+
 const char* ffb_last_error(const ffb_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
 
 int ffb_create(int device, ffb_ctx** out) {

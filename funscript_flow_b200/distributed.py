@@ -16,6 +16,40 @@ def world() -> (int, int):
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
 
+def _parse_cpulist(text: str) -> List[int]:
+    cpus: List[int] = []
+    for part in text.strip().split(","):
+        if "-" in part:
+            a, b = part.split("-")
+            cpus.extend(range(int(a), int(b) + 1))
+        elif part:
+            cpus.append(int(part))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device: Optional[int] = None, sysfs: str = "/sys") -> Optional[int]:
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, so that the pinned staging buffers
+    (first touch) and the upload threads are local to the GPU's PCIe root.  Call before the context is
+    created.  Returns the node, or None when the topology is flat / unknown (nothing is changed then)."""
+    from . import _native
+    dev = api.default_device() if device is None else int(device)
+    try:
+        bus = _native.device_pci_bus_id(dev)
+        if not bus:
+            return None
+        node = int(open(os.path.join(sysfs, "bus/pci/devices", bus, "numa_node")).read().strip())
+        if node < 0:
+            return None
+        cpus = set(_parse_cpulist(open(os.path.join(sysfs, "devices/system/node", f"node{node}", "cpulist")).read()))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except (OSError, ValueError, AttributeError):
+        return None
+
+
 def init(backend: Optional[str] = None):
     """Initialise torch.distributed from the torchrun environment (NCCL on GPU boxes, gloo on CPU)."""
     import torch

@@ -298,6 +298,9 @@ def run_headless(input_path: str, settings: Dict, log_func: Optional[Callable[[s
             logf.write(msg + "\n")
             logf.flush()
             print(msg)
+    if world > 1:       # one process per GPU: keep the host side on the GPU's NUMA node
+        from . import distributed
+        distributed.bind_to_gpu_numa_node()
     vids = list_videos(input_path)
     if world > 1:
         vids = schedule_longest_first(vids, [video_cost(v) for v in vids], world)[rank]

@@ -93,3 +93,30 @@ def test_cli_settings_match_reference_quirks():
     # extension keys (row N4) appear only when asked for
     s = settings_from_args(build_parser().parse_args(["clip.mp4", "--native_resolution", "--vr_mode", "--vr_eye", "right"]))
     assert s["native_resolution"] is True and s["vr_eye"] == "right"
+
+
+def test_numa_binding_reads_sysfs(tmp_path, emu_lib, monkeypatch):
+    """bind_to_gpu_numa_node: bus id from the C ABI -> numa_node -> cpulist -> sched_setaffinity; a flat or
+    unknown topology changes nothing."""
+    from funscript_flow_b200 import _native, distributed
+    assert distributed._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    monkeypatch.setattr(_native, "device_pci_bus_id", lambda dev=0, lib_path=None: "0000:1b:00.0")
+    before = os.sched_getaffinity(0)
+    dev = tmp_path / "bus/pci/devices/0000:1b:00.0"
+    dev.mkdir(parents=True)
+    (dev / "numa_node").write_text("-1\n")
+    assert distributed.bind_to_gpu_numa_node(0, sysfs=str(tmp_path)) is None and os.sched_getaffinity(0) == before
+    (dev / "numa_node").write_text("1\n")
+    assert distributed.bind_to_gpu_numa_node(0, sysfs=str(tmp_path)) is None        # node directory missing
+    node = tmp_path / "devices/system/node/node1"
+    node.mkdir(parents=True)
+    keep = sorted(before)[:max(1, len(before) // 2)]
+    (node / "cpulist").write_text(",".join(str(c) for c in keep) + "\n")
+    try:
+        assert distributed.bind_to_gpu_numa_node(0, sysfs=str(tmp_path)) == 1
+        assert os.sched_getaffinity(0) == set(keep)
+    finally:
+        os.sched_setaffinity(0, before)
+    lib = _native.load(emu_lib)
+    monkeypatch.undo()
+    assert _native.device_pci_bus_id(0, lib_path=emu_lib) == "0000:00:00.0"
