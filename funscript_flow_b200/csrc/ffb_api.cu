@@ -684,10 +684,8 @@ int configure(ffb_ctx* c, int W, int H, int B, int maxPairs) {
         L.taps = make_taps(L.ksize, L.sigma);
         TRY(build_level_tables(c, L, W, H, l > 0 ? c->lev[l - 1].w : 0, l > 0 ? c->lev[l - 1].h : 0));
         TRY(dev_alloc(c, &L.I, (size_t)(B + 1) * L.plane));
-        if (l < p.n - 1 || true) {
-            TRY(dev_alloc(c, &L.fA, (size_t)B * L.fp * L.h));
-            TRY(dev_alloc(c, &L.fB, (size_t)B * L.fp * L.h));
-        }
+        TRY(dev_alloc(c, &L.fA, (size_t)B * L.fp * L.h));
+        TRY(dev_alloc(c, &L.fB, (size_t)B * L.fp * L.h));
     }
     c->r_slot_floats = (off + 127) / 128 * 128;      // 512-byte multiples: texture views of the elements need it
     TRY(dev_alloc(c, &c->R, (size_t)c->S * c->r_slot_floats));
