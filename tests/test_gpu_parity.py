@@ -233,3 +233,28 @@ def test_process_video_matches_reference_funscript(gpu_ctx, golden_dir, tmp_path
     logs.clear()
     assert runner.process_video(path, dict(g["settings"], overwrite=False), logs.append) is False
     assert any("Skipping" in l for l in logs)
+
+
+@pytest.mark.gpu
+def test_process_video_modes_match_reference_funscripts(gpu_ctx, golden_dir, tmp_path):
+    """VR mode, POV mode and a 60 fps container (step-2 sub-sampling) through process_video(): device
+    pre-processing + hot path + host post-processing give the keyframe timestamps the reference wrote
+    (tests/golden/video_modes.json), positions within one unit."""
+    api.set_context(gpu_ctx)
+    g = json.load(open(os.path.join(golden_dir, "video_modes.json")))
+    for case in g["cases"]:
+        sp = case["spec"]
+        clip = ClipGenerator(ClipSpec(sp["width"], sp["height"], sp["n_frames"], seed=sp["seed"], amplitude=sp["amplitude"],
+                                      period=sp["period"])).stack()
+        path = str(tmp_path / (case["name"] + ".avi"))
+        vw = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"FFV1"), case["fps"], (sp["width"], sp["height"]), True)
+        if not vw.isOpened():
+            pytest.skip("FFV1 writer unavailable on this box")
+        for f in clip:
+            vw.write(cv2.cvtColor(f, cv2.COLOR_GRAY2BGR))
+        vw.release()
+        logs = []
+        assert runner.process_video(path, case["settings"], logs.append) is False, logs
+        acts = json.load(open(str(tmp_path / (case["name"] + ".funscript"))))["actions"]
+        assert [a["at"] for a in acts] == [a["at"] for a in case["actions"]], (case["name"], acts, case["actions"])
+        assert max(abs(a["pos"] - b["pos"]) for a, b in zip(acts, case["actions"])) <= 1, case["name"]

@@ -133,3 +133,29 @@ def test_preprocess_oracle_bit_exact_vs_cv2():
         rgb = cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
         want = cv2.cvtColor(np.ascontiguousarray(cv2.resize(rgb, target)[y:y + hh, x:x + ww]), cv2.COLOR_RGB2GRAY)
         assert np.array_equal(want, pp.frame_window_to_gray(img, target, (x, y, ww, hh))), (h, w, target)
+
+
+def _mode_clip(case):
+    from funscript_flow_b200.synth import ClipGenerator, ClipSpec
+    sp = case["spec"]
+    return ClipGenerator(ClipSpec(sp["width"], sp["height"], sp["n_frames"], seed=sp["seed"], amplitude=sp["amplitude"],
+                                  period=sp["period"])).stack()
+
+
+def test_oracle_pipeline_vs_golden_video_modes(golden_dir):
+    """The whole oracle chain (pre-processing restatement -> cv2 flow -> motion functions -> post-processing)
+    reproduces the funscripts the reference's process_video() wrote in VR mode, POV mode and from a 60 fps
+    container (tests/golden/video_modes.json, recorded from the reference itself).  FFV1 is lossless, so the
+    decoded frames are the generated clip."""
+    import math
+    from oracle import preproc_np as pp
+    g = json.load(open(os.path.join(golden_dir, "video_modes.json")))
+    for case in g["cases"]:
+        st = case["settings"]
+        clip = _mode_clip(case)
+        step = max(1, int(math.ceil(case["fps"] / 30.0)))
+        idx = list(range(0, len(clip), step))
+        gray = [pp.frame_to_gray(cv2.cvtColor(clip[i], cv2.COLOR_GRAY2BGR), st["vr_mode"]) for i in idx]
+        vals, cuts, _ = mo.process_bracket(gray, st)
+        acts = mo.postprocess([(float(vals[j]), bool(cuts[j]), idx[j]) for j in range(len(vals))], case["fps"], st)
+        assert acts == case["actions"], case["name"]
