@@ -42,7 +42,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
-    ap.add_argument("--pairs-per-step", type=int, default=128)
+    ap.add_argument("--pairs-per-step", type=int, default=256,
+                    help="pairs of one bracket = one step (the reference's brackets hold 3000 frames, F:2661)")
     ap.add_argument("--batch-frames", type=int, default=64)
     ap.add_argument("--cpu-sample-pairs", type=int, default=0, help="0 = 2 x host cores (bounded to 8..64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

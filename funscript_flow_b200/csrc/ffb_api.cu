@@ -547,7 +547,7 @@ int launch_flow_iter_t(ffb_ctx* c, FfbIterArgs a, int npairs, int sh_target, dou
     if (nseg < min_seg) nseg = min_seg;
     if (nseg > (h + 31) / 32) nseg = (h + 31) / 32;
     if (nseg < 1) nseg = 1;
-    a.SH = (h + nseg - 1) / nseg;
+    a.SH = ffb_round_up((h + nseg - 1) / nseg, 2);     // even: see the fused up-sampling in k_flow_iter
     const int gy = (h + a.SH - 1) / a.SH;
     auto kfn = a.up_src ? k_flow_iter<NT, U, MINB, HFIRST, true, HO, CL, TX> : k_flow_iter<NT, U, MINB, HFIRST, false, HO, CL, TX>;
     const size_t smem = ffb_flow_iter_smem<NT, U, CL>();

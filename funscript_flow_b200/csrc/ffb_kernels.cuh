@@ -852,6 +852,34 @@ __global__ void __launch_bounds__(NT, MINB) k_flow_iter(FfbIterArgs a) {
     float ual = 0.f;
     if (UP2X) ffb_up2(xc, a.wc, ux0, ux1, ual);
     auto load_flow = [&](int s, float2 (&d)[U]) {
+        if (UP2X && U == 2) {
+            // The launcher makes SH even, so the two rows of a step are an (odd, even) pair of image rows (or
+            // both clamped to the same border row): they interpolate between the SAME two coarse rows, with
+            // weights 0.25 / 0.75.  Fetch and x-interpolate those rows once for both.
+            const int ya = ffb_clampi(y0 - FFB_WIN_R + s * 2, 0, h - 1), yb = ffb_clampi(y0 - FFB_WIN_R + s * 2 + 1, 0, h - 1);
+            int uy0, uy1, vy0, vy1;
+            float be0, be1;
+            ffb_up2(ya, a.hc, uy0, uy1, be0);
+            ffb_up2(yb, a.hc, vy0, vy1, be1);
+            const float2 p00 = __ldg(ups + (uy0 * a.usp + ux0)), p01 = __ldg(ups + (uy0 * a.usp + ux1));
+            const float2 p10 = __ldg(ups + (uy1 * a.usp + ux0)), p11 = __ldg(ups + (uy1 * a.usp + ux1));
+            const float tx = p00.x * (1.f - ual) + p01.x * ual, ty = p00.y * (1.f - ual) + p01.y * ual;
+            const float bx = p10.x * (1.f - ual) + p11.x * ual, by = p10.y * (1.f - ual) + p11.y * ual;
+            d[0].x = (tx * (1.f - be0) + bx * be0) * 2.f;
+            d[0].y = (ty * (1.f - be0) + by * be0) * 2.f;
+            if (vy0 == uy0 && vy1 == uy1) {
+                d[1].x = (tx * (1.f - be1) + bx * be1) * 2.f;
+                d[1].y = (ty * (1.f - be1) + by * be1) * 2.f;
+            } else {   // not reached with an even SH; kept so that any segmentation stays correct
+                const float2 q00 = __ldg(ups + (vy0 * a.usp + ux0)), q01 = __ldg(ups + (vy0 * a.usp + ux1));
+                const float2 q10 = __ldg(ups + (vy1 * a.usp + ux0)), q11 = __ldg(ups + (vy1 * a.usp + ux1));
+                const float sx = q00.x * (1.f - ual) + q01.x * ual, sy = q00.y * (1.f - ual) + q01.y * ual;
+                const float cx = q10.x * (1.f - ual) + q11.x * ual, cy = q10.y * (1.f - ual) + q11.y * ual;
+                d[1].x = (sx * (1.f - be1) + cx * be1) * 2.f;
+                d[1].y = (sy * (1.f - be1) + cy * be1) * 2.f;
+            }
+            return;
+        }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int yc = ffb_clampi(y0 - FFB_WIN_R + s * U + u, 0, h - 1);
