@@ -2,7 +2,7 @@
 
     python -m funscript_flow_b200 INPUT [--threads N] [--detrend_window S] [--norm_window S] [--batch_size N]
                                   [--overwrite] [--vr_mode] [--pov_mode] [--disable_keyframe_reduction]
-                                  [--native_resolution] [--vr_eye left|right]      (extensions)
+                                  [--native_resolution] [--vr_eye left|right|both]      (extensions)
 
 Under `torchrun --nproc-per-node N` every rank takes each N-th video of the folder on its own GPU.
 The reference's quirk is kept: `--disable_keyframe_reduction` is a store_false flag whose
@@ -31,7 +31,8 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--backend", default="CUDA", help="accepted for compatibility; there is one backend")
     # extensions the reference has no equivalent of (runner.preprocess_plan)
     p.add_argument("--native_resolution", action="store_true", help="run the flow on the decoded frame size instead of 256x256")
-    p.add_argument("--vr_eye", choices=["left", "right"], default="left", help="which eye of a side-by-side VR frame (with --vr_mode)")
+    p.add_argument("--vr_eye", choices=["left", "right", "both"], default="left",
+                   help="which eye of a side-by-side VR frame (with --vr_mode); both = mean of the two eyes' scalars")
     return p
 
 

@@ -153,6 +153,7 @@ class FlowContext:
 
     def __init__(self, device: int = 0, lib_path: Optional[str] = None):
         self._lib = load(lib_path)
+        self.lib_path = lib_path
         h = C.c_void_p()
         rc = self._lib.ffb_create(int(device), C.byref(h))
         if rc:

@@ -47,6 +47,21 @@ def get_context(device: Optional[int] = None) -> _native.FlowContext:
     return ctx
 
 
+_aux_contexts: Dict[int, _native.FlowContext] = {}
+
+
+def get_aux_context(primary: _native.FlowContext) -> _native.FlowContext:
+    """A second context on the device (and from the library) of `primary`, for work that runs beside it:
+    the other eye of a side-by-side VR frame (runner, vr_eye="both")."""
+    key = id(primary)
+    ctx = _aux_contexts.get(key)
+    if ctx is None:
+        ctx = _native.FlowContext(primary.device, lib_path=primary.lib_path)
+        _aux_contexts.clear()          # one auxiliary context at a time
+        _aux_contexts[key] = ctx
+    return ctx
+
+
 def set_context(ctx: _native.FlowContext, device: int = 0) -> None:
     """Install an externally created context (tests use this to inject the emulated library)."""
     _contexts[int(device)] = ctx

@@ -100,7 +100,7 @@ def read_sampled_gray(video_path: str, indices: Sequence[int], params: Dict) -> 
     return out
 
 
-def preprocess_plan(src_w: int, src_h: int, params: Dict):
+def preprocess_plan(src_w: int, src_h: int, params: Dict, eye: Optional[str] = None):
     """(target, window, cut_scale) of the frame contract for `params`.
 
     Reference modes: resize to 256x256 (F:1057) or, with `vr_mode`, to 512x512 and keep the bottom-left
@@ -109,12 +109,15 @@ def preprocess_plan(src_w: int, src_h: int, params: Dict):
                          one eye of the side-by-side frame); `cut_threshold` (F:876, tuned for 256x256
                          frames) is multiplied by cut_scale = sqrt(w*h)/256 because flow magnitudes
                          are in pixels;
-      vr_eye             "left" (the reference's choice) or "right".
+      vr_eye             "left" (the reference's choice), "right", or "both": process_video_series then runs
+                         the two eyes as two independent series on two contexts of the same GPU (one decode,
+                         every chunk pushed to both) and reports the mean scalar and the OR of the cut flags.
+                         For "both" this function returns the left eye's plan; `eye` overrides params.
     """
     vr = bool(params.get("vr_mode"))
-    eye = str(params.get("vr_eye", "left")).lower()
-    if eye not in ("left", "right"):
-        raise ValueError("vr_eye must be 'left' or 'right'")
+    eye = str(eye if eye is not None else params.get("vr_eye", "left")).lower()
+    if eye not in ("left", "right", "both"):
+        raise ValueError("vr_eye must be 'left', 'right' or 'both'")
     right = vr and eye == "right"
     if params.get("native_resolution"):
         if vr:
@@ -141,6 +144,7 @@ def process_video_series(video_path: str, params: Dict, ctx=None, progress_callb
     hot path.  Returns (values, cuts, frame_indices, fps) or None when cancelled."""
     import cv2
     ctx = ctx or api.get_context()
+    both = bool(params.get("vr_mode")) and str(params.get("vr_eye", "left")).lower() == "both"
     cap = cv2.VideoCapture(video_path)
     if not cap.isOpened():
         raise IOError(f"cannot open {video_path}")
@@ -150,9 +154,14 @@ def process_video_series(video_path: str, params: Dict, ctx=None, progress_callb
     cap.release()
     if total < 2 or fps <= 0 or src_w < 2 or src_h < 2:
         raise IOError("unable to read video properties")
-    target, window, cut_scale = preprocess_plan(src_w, src_h, params)
+    target, window, cut_scale = preprocess_plan(src_w, src_h, params, "left" if both else None)
     out_w, out_h = window[2], window[3]
     ctx.preprocess_configure_window(src_w, src_h, target, window)
+    ctxs = [ctx]
+    if both:      # the other eye: same geometry, its own context (streams, rings) on the same device
+        ctx_r = api.get_aux_context(ctx)
+        ctx_r.preprocess_configure_window(src_w, src_h, *preprocess_plan(src_w, src_h, params, "right")[:2])
+        ctxs.append(ctx_r)
     cut_threshold = float(params.get("cut_threshold", api.DEFAULT_CUT_THRESHOLD)) * cut_scale
     step = postproc.sampling_step(fps)
     indices = list(range(0, total, step))
@@ -173,8 +182,9 @@ def process_video_series(video_path: str, params: Dict, ctx=None, progress_callb
             for _ in range(nfr):
                 next(frames, None)
             continue
-        ctx.configure(out_w, out_h, max(1, min(batch, nfr)), nfr - 1)
-        ctx.bracket_begin(bool(params.get("pov_mode", False)), cut_threshold)
+        for c in ctxs:
+            c.configure(out_w, out_h, max(1, min(batch, nfr)), nfr - 1)
+            c.bracket_begin(bool(params.get("pov_mode", False)), cut_threshold)
         got = 0
         while got < nfr:
             chunk = []
@@ -187,16 +197,23 @@ def process_video_series(video_path: str, params: Dict, ctx=None, progress_callb
                 break
             arr = np.ascontiguousarray(np.stack(chunk))
             if arr.shape[1:3] != (src_h, src_w):
-                ctx.bracket_finish()
+                for c in ctxs:
+                    c.bracket_finish()
                 raise IOError(f"decoded frame size {arr.shape[2]}x{arr.shape[1]} differs from the container's {src_w}x{src_h}")
-            ctx.bracket_push_bgr(arr)   # pageable input is copied into pinned staging before the call returns
+            for c in ctxs:
+                c.bracket_push_bgr(arr)   # pageable input is copied into pinned staging before the call returns
             got += len(chunk)
             done += len(chunk)
             if progress_callback:
                 progress_callback(min(100, int(100 * done / len(indices))))
-        r = ctx.bracket_finish()
-        values.extend(r["scalar"].tolist())
-        cuts.extend(r["cut"].tolist())
+        rs = [c.bracket_finish() for c in ctxs]
+        r = rs[0]
+        if both:
+            values.extend((0.5 * (rs[0]["scalar"] + rs[1]["scalar"])).tolist())
+            cuts.extend((rs[0]["cut"].astype(bool) | rs[1]["cut"].astype(bool)).tolist())
+        else:
+            values.extend(r["scalar"].tolist())
+            cuts.extend(r["cut"].tolist())
         stamps.extend(indices[a:a + r["n_pairs"]])
     return values, cuts, stamps, fps
 

@@ -73,7 +73,8 @@ def test_preprocess_window_and_native_resolution(emu_ctx):
     with pytest.raises(Exception):
         emu_ctx.preprocess_configure_window(96, 64, (96, 64), (50, 0, 96, 64))    # window leaves the target
     with pytest.raises(ValueError):
-        runner.preprocess_plan(96, 64, {"vr_mode": True, "vr_eye": "both"})
+        runner.preprocess_plan(96, 64, {"vr_mode": True, "vr_eye": "up"})
+    assert runner.preprocess_plan(96, 64, {"vr_mode": True, "vr_eye": "both"}) == runner.preprocess_plan(96, 64, {"vr_mode": True})
     assert runner.preprocess_plan(1920, 1080, {}) == ((256, 256), (0, 0, 256, 256), 1.0)
     assert runner.preprocess_plan(1920, 1080, {"vr_mode": True}) == ((512, 512), (0, 256, 256, 256), 1.0)
     assert runner.preprocess_plan(1920, 1080, {"vr_mode": True, "vr_eye": "right"})[1] == (256, 256, 256, 256)
@@ -108,6 +109,14 @@ def test_process_video_file(emu_ctx, tmp_path):
     res = runner.process_video_series(path, dict(prm, native_resolution=True), ctx=emu_ctx)
     direct = api.process_bracket(clip, {"cut_threshold": 7.0 * np.sqrt(160 * 120) / 256.0}, ctx=emu_ctx, batch_frames=4)
     assert res[0] == direct["scalar"].tolist() and res[1] == direct["cut"].tolist()
+    # both eyes of a side-by-side frame = mean of the two single-eye series (two contexts, one decode)
+    vr = dict(prm, vr_mode=True, native_resolution=True)
+    left = runner.process_video_series(path, dict(vr, vr_eye="left"), ctx=emu_ctx)
+    right = runner.process_video_series(path, dict(vr, vr_eye="right"), ctx=emu_ctx)
+    both = runner.process_video_series(path, dict(vr, vr_eye="both"), ctx=emu_ctx)
+    assert left[0] != right[0]
+    assert both[0] == (0.5 * (np.asarray(left[0]) + np.asarray(right[0]))).tolist()
+    assert both[1] == [a or b for a, b in zip(left[1], right[1])] and both[2] == left[2]
 
 
 def test_headless_folder_sharded_over_ranks(emu_ctx, tmp_path, monkeypatch):
