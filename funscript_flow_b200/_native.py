@@ -53,6 +53,7 @@ def load(path: Optional[str] = None) -> C.CDLL:
         "ffb_bracket_push": (i32, [vp, vp, i32, sz, sz]),
         "ffb_bracket_finish": (i32, [vp, i32p, f64p, u8p, i32p, i32p, f32p, f32p, f64p]),
         "ffb_sync": (i32, [vp]),
+        "ffb_bracket_abort": (i32, [vp]),
         "ffb_bracket_get_flow": (i32, [vp, i32, f32p]),
         "ffb_flow_ring_size": (i32, [vp]),
         "ffb_farneback": (i32, [vp, u8p, u8p, i32, i32, sz, f32p]),
@@ -240,6 +241,10 @@ class FlowContext:
         self._ck(self._lib.ffb_stage_preprocess_window(self._h, _u8(bgr), w, h, w * 3, int(target[0]), int(target[1]),
                                                        *(int(v) for v in window), _u8(out)))
         return out
+
+    def bracket_abort(self):
+        """Drop the open bracket (error path / cancel); the context can be configured again afterwards."""
+        self._ck(self._lib.ffb_bracket_abort(self._h))
 
     def bracket_finish(self):
         m = self.geometry[3]

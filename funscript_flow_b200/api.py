@@ -101,7 +101,11 @@ def process_bracket(frames, params: Optional[Dict] = None, *, ctx: Optional[_nat
     n, h, w = arr.shape
     ctx.configure(w, h, max(1, min(batch_frames, n)), max(n - 1, 1))
     ctx.bracket_begin(bool(params.get("pov_mode", False)), float(params.get("cut_threshold", DEFAULT_CUT_THRESHOLD)))
-    ctx.bracket_push(arr)
+    try:
+        ctx.bracket_push(arr)
+    except BaseException:
+        ctx.bracket_abort()      # leave the context usable
+        raise
     res = ctx.bracket_finish()
     if return_flows:
         k = res["n_pairs"]
@@ -123,8 +127,12 @@ def precompute_flow_info(p0: np.ndarray, p1: np.ndarray, config: Dict) -> Dict:
     pov = bool(config.get("pov_mode"))
     ctx.configure(w, h, 2, 64)
     ctx.bracket_begin(pov, float(config.get("cut_threshold", DEFAULT_CUT_THRESHOLD)))
-    ctx.bracket_push(p0)
-    ctx.bracket_push(p1)
+    try:
+        ctx.bracket_push(p0)
+        ctx.bracket_push(p1)
+    except BaseException:
+        ctx.bracket_abort()
+        raise
     r = ctx.bracket_finish()
     flow = ctx.get_flow(0)
     if pov:   # F:882: plain Python ints and the int 0

@@ -1235,6 +1235,20 @@ int ffb_bracket_push(ffb_ctx* c, const uint8_t* frames, int n, size_t pitch, siz
     return FFB_OK;
 }
 
+int ffb_bracket_abort(ffb_ctx* c) {
+    if (!c) return FFB_E_INVALID;
+    if (!c->in_bracket) return FFB_OK;
+    cudaSetDevice(c->device);
+    // queued work reads the caller's buffers and the staging rings: let it drain (errors are already recorded)
+    cudaStreamSynchronize(c->s_copy);
+    cudaStreamSynchronize(c->s_comp);
+    for (int i = 0; i < 3; ++i) cudaStreamSynchronize(c->s_aux[i]);
+    cudaGetLastError();
+    c->in_bracket = false;
+    c->frames_seen = c->pairs_done = c->radial_done = 0;
+    return FFB_OK;
+}
+
 int ffb_sync(ffb_ctx* c) {
     if (!c) return FFB_E_INVALID;
     CK(c, cudaStreamSynchronize(c->s_copy));

@@ -185,27 +185,34 @@ def process_video_series(video_path: str, params: Dict, ctx=None, progress_callb
         for c in ctxs:
             c.configure(out_w, out_h, max(1, min(batch, nfr)), nfr - 1)
             c.bracket_begin(bool(params.get("pov_mode", False)), cut_threshold)
-        got = 0
-        while got < nfr:
-            chunk = []
-            while len(chunk) < chunk_frames and got + len(chunk) < nfr:
-                f = next(frames, None)
-                if f is None:
+        try:
+            got = 0
+            while got < nfr:
+                if cancel_flag and cancel_flag():      # F:1147-1149, checked per chunk instead of per bracket
+                    for c in ctxs:
+                        c.bracket_abort()
+                    return None
+                chunk = []
+                while len(chunk) < chunk_frames and got + len(chunk) < nfr:
+                    f = next(frames, None)
+                    if f is None:
+                        break
+                    chunk.append(f)
+                if not chunk:
                     break
-                chunk.append(f)
-            if not chunk:
-                break
-            arr = np.ascontiguousarray(np.stack(chunk))
-            if arr.shape[1:3] != (src_h, src_w):
+                arr = np.ascontiguousarray(np.stack(chunk))
+                if arr.shape[1:3] != (src_h, src_w):
+                    raise IOError(f"decoded frame size {arr.shape[2]}x{arr.shape[1]} differs from the container's {src_w}x{src_h}")
                 for c in ctxs:
-                    c.bracket_finish()
-                raise IOError(f"decoded frame size {arr.shape[2]}x{arr.shape[1]} differs from the container's {src_w}x{src_h}")
-            for c in ctxs:
-                c.bracket_push_bgr(arr)   # pageable input is copied into pinned staging before the call returns
-            got += len(chunk)
-            done += len(chunk)
-            if progress_callback:
-                progress_callback(min(100, int(100 * done / len(indices))))
+                    c.bracket_push_bgr(arr)   # pageable input is copied into pinned staging before the call returns
+                got += len(chunk)
+                done += len(chunk)
+                if progress_callback:
+                    progress_callback(min(100, int(100 * done / len(indices))))
+        except BaseException:
+            for c in ctxs:      # leave the contexts usable for the next video
+                c.bracket_abort()
+            raise
         rs = [c.bracket_finish() for c in ctxs]
         r = rs[0]
         if both:

@@ -86,6 +86,10 @@ int  ffb_bracket_begin(ffb_ctx* ctx, int pov_mode, double cut_threshold);
 int  ffb_bracket_push(ffb_ctx* ctx, const uint8_t* frames, int n_frames, size_t pitch, size_t frame_stride);
 int  ffb_bracket_finish(ffb_ctx* ctx, int* n_pairs, double* scalar, uint8_t* cut, int32_t* cx, int32_t* cy,
                         float* val, float* mean_mag, double* centers);
+/* Drop the open bracket without results (after an error, or on user cancel: F:1147-1149 "User bailed"):
+ * waits for the device work already queued, then leaves the context ready for ffb_bracket_begin /
+ * ffb_configure.  A no-op outside a bracket. */
+int  ffb_bracket_abort(ffb_ctx* ctx);
 /* Block until all uploads issued so far have left the caller's buffers. */
 int  ffb_sync(ffb_ctx* ctx);
 /* Copy the final flow field of pair `pair` of the current / last bracket to host (test hook and

@@ -200,3 +200,40 @@ def test_error_paths_and_strided_input(emu_ctx):
     got = emu_ctx.bracket_finish()
     for k in ("scalar", "cx", "cy", "val", "mean_mag"):
         assert np.array_equal(ref[k], got[k]), k
+
+
+def test_bracket_abort_and_cancel(emu_ctx, tmp_path):
+    """ffb_bracket_abort drops an open bracket and leaves the context configurable; the runner uses it when the
+    user cancels (F:1147-1149) or a chunk fails, so the next video is not refused with 'inside a bracket'."""
+    import cv2
+    clip = make_clip(96, 64, 7, seed=31)
+    full = api.process_bracket(clip, {}, ctx=emu_ctx, batch_frames=3)
+    emu_ctx.configure(96, 64, 3, 6)
+    emu_ctx.bracket_begin(False, 7.0)
+    emu_ctx.bracket_push(clip[:4])
+    with pytest.raises(Exception, match="inside a bracket|in a bracket|bracket"):
+        emu_ctx.preprocess_configure(96, 64, False)
+    emu_ctx.bracket_abort()
+    emu_ctx.bracket_abort()                                   # no-op outside a bracket
+    emu_ctx.preprocess_configure(96, 64, False)               # accepted again
+    again = api.process_bracket(clip, {}, ctx=emu_ctx, batch_frames=3)
+    assert np.array_equal(full["scalar"], again["scalar"])    # nothing of the dropped bracket leaks into the next
+    # runner: cancel in the middle of a bracket, then process the same file normally
+    api.set_context(emu_ctx)
+    path = str(tmp_path / "c.avi")
+    vw = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"FFV1"), 30.0, (96, 64), True)
+    if not vw.isOpened():
+        pytest.skip("FFV1 writer unavailable")
+    for f in clip:
+        vw.write(cv2.cvtColor(f, cv2.COLOR_GRAY2BGR))
+    vw.release()
+    prm = {"batch_size": 3000, "detrend_window": 2.0, "norm_window": 3.0, "keyframe_reduction": False, "overwrite": True,
+           "vr_mode": False, "pov_mode": False, "gpu_batch_frames": 3}
+    calls = {"n": 0}
+
+    def cancel_after_first_chunk():
+        calls["n"] += 1
+        return calls["n"] > 2
+    assert runner.process_video_series(path, prm, ctx=emu_ctx, cancel_flag=cancel_after_first_chunk, chunk_frames=3) is None
+    logs = []
+    assert runner.process_video(path, prm, logs.append) is False, logs
