@@ -258,3 +258,35 @@ def test_process_video_modes_match_reference_funscripts(gpu_ctx, golden_dir, tmp
         acts = json.load(open(str(tmp_path / (case["name"] + ".funscript"))))["actions"]
         assert [a["at"] for a in acts] == [a["at"] for a in case["actions"]], (case["name"], acts, case["actions"])
         assert max(abs(a["pos"] - b["pos"]) for a, b in zip(acts, case["actions"])) <= 1, case["name"]
+
+
+@pytest.mark.gpu
+def test_both_eyes_two_contexts_and_abort(gpu_ctx, tmp_path):
+    """Row N4 on the device: vr_eye="both" drives two contexts on one GPU from one decode and equals the mean
+    of the single-eye runs; an aborted bracket leaves no trace in the next one."""
+    api.set_context(gpu_ctx)
+    clip = make_clip(640, 320, 12, seed=41, period=9.0, amplitude=0.3)
+    path = str(tmp_path / "sbs.avi")
+    vw = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"FFV1"), 30.0, (640, 320), True)
+    if not vw.isOpened():
+        pytest.skip("FFV1 writer unavailable on this box")
+    for f in clip:
+        vw.write(cv2.cvtColor(f, cv2.COLOR_GRAY2BGR))
+    vw.release()
+    for native in (False, True):
+        prm = {"batch_size": 3000, "vr_mode": True, "pov_mode": False, "gpu_batch_frames": 5, "native_resolution": native}
+        left = runner.process_video_series(path, dict(prm, vr_eye="left"), ctx=gpu_ctx)
+        right = runner.process_video_series(path, dict(prm, vr_eye="right"), ctx=gpu_ctx)
+        both = runner.process_video_series(path, dict(prm, vr_eye="both"), ctx=gpu_ctx)
+        assert left[0] != right[0]
+        assert both[0] == (0.5 * (np.asarray(left[0]) + np.asarray(right[0]))).tolist()
+        assert both[1] == [a or b for a, b in zip(left[1], right[1])]
+    gray = make_clip(320, 200, 9, seed=42)
+    full = api.process_bracket(gray, {}, ctx=gpu_ctx, batch_frames=4)
+    gpu_ctx.configure(320, 200, 4, 8)
+    gpu_ctx.bracket_begin(False, 7.0)
+    gpu_ctx.bracket_push(gray[:6])
+    gpu_ctx.bracket_abort()
+    again = api.process_bracket(gray, {}, ctx=gpu_ctx, batch_frames=4)
+    for k in ("scalar", "cut", "cx", "cy", "val", "mean_mag"):
+        assert np.array_equal(full[k], again[k]), k
