@@ -201,6 +201,7 @@ struct ffb_ctx {
     std::vector<cudaTextureObject_t> h_tex4, h_tex1;
     cudaTextureObject_t *d_tex4 = nullptr, *d_tex1 = nullptr;
     int iter_tex = 0;      // TX variant used by the bracket path (0 = LSU loads only)
+    long long seg_frame_px = 0;      // pixels of the frame whose levels are being iterated (segmentation rule)
     float2* ring = nullptr;
     size_t ring_stride = 0;   // float2 per ring element
     uint8_t* d_u8[2] = {nullptr, nullptr};
@@ -543,10 +544,12 @@ int launch_flow_iter_t(ffb_ctx* c, FfbIterArgs a, int npairs, int sh_target, dou
     // at most sh_target rows per segment, at least min_seg segments per level (coarse levels would
     // otherwise be a handful of long, latency-bound marches), never under 32 rows
     static const int min_seg_env = getenv("FFB_ITER_MINSEG") ? atoi(getenv("FFB_ITER_MINSEG")) : 0;
-    // levels of 512 rows and more: 4 segments (parallelism for the 64-pair batches of large frames); smaller levels:
-    // 2 (small frames come in large batches, and every segment pays 14 halo rows): +7 % at 256x256, +3.5 % at 640x360,
-    // +-0 at 1080p / 4K (profiles/r1_sweep_segments.txt)
-    const int min_seg = min_seg_env > 0 ? min_seg_env : (h >= 512 ? 4 : 2);
+    // frames of 1280x720 and more: 4 segments on every level (parallelism for their 64-pair batches); smaller frames
+    // come in batches of hundreds, and every segment pays 14 halo rows: 2 (+7 % at 256x256, +3.5 % at 640x360;
+    // at 1080p 2 segments on the coarse levels lose 0.5 %: profiles/r1_sweep_segments.txt).  The rule looks at the
+    // frame the context is configured for, never at the batch.
+    const long long frame_px = c->seg_frame_px > 0 ? c->seg_frame_px : (long long)w * h;      // stage hooks: the level itself
+    const int min_seg = min_seg_env > 0 ? min_seg_env : (frame_px >= 1280LL * 720 ? 4 : 2);
     int nseg = (h + sh_target - 1) / sh_target;
     if (nseg < min_seg) nseg = min_seg;
     if (nseg > (h + 31) / 32) nseg = (h + 31) / 32;
@@ -796,6 +799,7 @@ int launch_divmag(ffb_ctx* c, int p0, int off, int cnt, cudaStream_t stream);
 
 int flow_pairs(ffb_ctx* c, int p0, int np) {
     c->phase_timing = false;
+    c->seg_frame_px = (long long)c->W * c->H;
     static const bool fuse_up = !(getenv("FFB_FUSE_UP") && atoi(getenv("FFB_FUSE_UP")) == 0);
     // FFB_FLOW_STREAMS=n (1..4): the pairs of a batch are split in n slices whose launch chains run on
     // n streams, so that the short coarse-level launches (and the tail of every launch) of one slice
@@ -876,6 +880,7 @@ int flow_pairs(ffb_ctx* c, int p0, int np) {
     }
     c->sliced_divmag = nslice > 1;
     c->cur_level = -1;
+    c->seg_frame_px = 0;
     return FFB_OK;
 }
 

@@ -132,9 +132,15 @@ def preprocess_plan(src_w: int, src_h: int, params: Dict, eye: Optional[str] = N
 
 
 def default_batch_frames(width: int, height: int) -> int:
-    """Frames per GPU batch: 64 up to 4K, fewer above so that the per-batch device buffers (about
-    64 bytes per pixel and frame) stay near 35 GB at any frame size."""
-    return max(2, min(64, int(64 * (3840 * 2160) / max(1, width * height))))
+    """Frames per GPU batch.  Small frames need many pairs per launch to fill 148 SMs (the reference's 256x256
+    product mode: 512), 1080p .. 4K run at full rate from 64, and above 4K the batch shrinks so that the
+    per-batch device buffers (about 64 bytes per pixel and frame) stay near 35 GB."""
+    px = max(1, width * height)
+    if px <= 640 * 360:
+        return 512
+    if px <= 1280 * 720:
+        return 128
+    return max(2, min(64, int(64 * (3840 * 2160) / px)))
 
 
 def process_video_series(video_path: str, params: Dict, ctx=None, progress_callback=None, cancel_flag=None,
