@@ -2,6 +2,8 @@
 emulation in tests/emu/, checked against the oracle on small inputs -- tiling, halos, ring buffers,
 batching and reductions are exercised before any GPU time is spent.  The real parity tests are the
 `-m gpu` ones; this file only proves the logic, not the sm_100a build."""
+import os
+
 import numpy as np
 import pytest
 
@@ -237,3 +239,23 @@ def test_bracket_abort_and_cancel(emu_ctx, tmp_path):
     assert runner.process_video_series(path, prm, ctx=emu_ctx, cancel_flag=cancel_after_first_chunk, chunk_frames=3) is None
     logs = []
     assert runner.process_video(path, prm, logs.append) is False, logs
+
+
+def test_integration_stub_from_the_docs_runs(emu_lib, emu_ctx):
+    """The ctypes stub INTEGRATION.md tells a reference maintainer to paste (replacement body of
+    precompute_flow_info_gpu, F:982-1017) is executed as written, against the emulated library, and returns
+    the same 8-key dict as the shipped Python mirror."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    code = re.search(r"```python\n(# --- in FunscriptFlow\.pyw.*?)```", text, re.S).group(1)
+    code = code.replace("/path/to/funscript_flow_b200/libffb.so", emu_lib)
+    ns = {}
+    exec(compile(code, "INTEGRATION.md", "exec"), ns)
+    clip = make_clip(96, 64, 2, seed=77)
+    got = ns["precompute_flow_info_gpu"](clip[0], clip[1], 7)
+    api.set_context(emu_ctx)
+    want = api.precompute_flow_info_gpu(clip[0], clip[1], 7)
+    assert set(got) == set(want) == {"flow", "pos_center", "neg_center", "val_pos", "val_neg", "cut", "cut_center", "mean_mag"}
+    assert np.array_equal(got["flow"], want["flow"]) and got["pos_center"] == want["pos_center"]
+    assert got["val_pos"] == want["val_pos"] and got["cut"] == want["cut"] and got["mean_mag"] == want["mean_mag"]
