@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import json
 import math
-from typing import Dict, List, Sequence
+from typing import Optional, Dict, List, Sequence
 
 import numpy as np
 
@@ -84,15 +84,22 @@ def keyframes(norm: np.ndarray, reduce: bool) -> List[int]:
 
 
 def scalars_to_actions(values: Sequence[float], cuts: Sequence[bool], frame_indices: Sequence[int], fps: float,
-                       params: Dict) -> List[Dict[str, int]]:
+                       params: Dict, errors: Optional[List[str]] = None) -> List[Dict[str, int]]:
     """The whole of F:1266-1386 for one video."""
     eff_fps = fps / sampling_step(fps)
     cum = integrate(values, cuts)
     det = detrend(cum, int(params["detrend_window"] * eff_fps))
     smooth = np.convolve(det, SMOOTH_TAPS, mode="same")
     norm = normalise(smooth, int(params["norm_window"] * eff_fps))
+    # np.convolve(mode="same") hands back max(n, 5) samples: for a series shorter than the 5-tap smoother the
+    # reference normalises and picks keyframes over those 5 samples and drops the indices without a time stamp
+    # (F:1379-1385, where it also flags the video as failed) -- kept as is; `errors` collects the dropped indices
     acts = []
     for k in keyframes(norm, bool(params["keyframe_reduction"])):
+        if k >= len(frame_indices):
+            if errors is not None:
+                errors.append(f"Error computing action at segment index {k}: list index out of range")
+            continue
         acts.append({"at": int((frame_indices[k] / fps) * 1000), "pos": 100 - int(round(norm[k]))})   # F:1380-1382
     return acts
 

@@ -252,7 +252,10 @@ def process_video(video_path, params, log_func, progress_callback=None, cancel_f
     values, cuts, stamps, fps = res
     step = postproc.sampling_step(fps)
     log_func(f"FPS: {fps:.2f}; downsampled to ~{fps / step:.2f} fps; {len(stamps) + 1} frames selected.")
-    actions = postproc.scalars_to_actions(values, cuts, stamps, fps, params) if values else []
+    errors: List[str] = []
+    actions = postproc.scalars_to_actions(values, cuts, stamps, fps, params, errors) if values else []
+    for msg in errors:           # F:1383-1385: series shorter than the smoother (fewer than 6 sampled frames)
+        log_func(msg)
     log_func(f"Keyframe reduction: {len(actions)} actions computed.")
     try:
         postproc.write_funscript(output_path, actions)
@@ -261,7 +264,7 @@ def process_video(video_path, params, log_func, progress_callback=None, cancel_f
         log_func(f"ERROR: {exc}")
         return True
     log_func(f"Processing time: {time.time() - start:.2f} seconds")
-    return False
+    return bool(errors)
 
 
 def list_videos(input_path: str) -> List[str]:

@@ -164,19 +164,24 @@ def postprocess(final_flow_list: List[Tuple[float, bool, int]], fps: float, para
     det = det / np.maximum(wsum, 1e-6)                           # F:1331
 
     sm = np.convolve(det, [1 / 16, 1 / 4, 3 / 8, 1 / 4, 1 / 16], mode="same")   # F:1333
+    # np.convolve(mode="same") returns max(n, 5) samples: for a series shorter than the smoother the reference
+    # carries on with 5 samples (F:1340, F:1369) and drops the actions whose index has no time stamp (the
+    # IndexError is caught at F:1383-1385) -- restated as is
+    m = len(sm)
     nwin = int(params["norm_window"] * eff_fps)                  # F:1335-1349
     if nwin % 2 == 0:
         nwin += 1
     hn = nwin // 2
-    norm = np.empty(n)
-    for i in range(n):
-        loc = sm[max(0, i - hn): min(n, i + hn + 1)]
+    norm = np.empty(m)
+    for i in range(m):
+        loc = sm[max(0, i - hn): min(m, i + hn + 1)]
         lo, hi = loc.min(), loc.max()
         norm[i] = 50 if hi - lo == 0 else (sm[i] - lo) / (hi - lo) * 100
 
     if params["keyframe_reduction"]:                             # F:1366-1376
-        keys = [0] + [i for i in range(1, n - 1)
-                      if ((norm[i] - norm[i - 1]) < 0) != ((norm[i + 1] - norm[i]) < 0)] + [n - 1]
+        keys = [0] + [i for i in range(1, m - 1)
+                      if ((norm[i] - norm[i - 1]) < 0) != ((norm[i + 1] - norm[i]) < 0)] + [m - 1]
     else:
-        keys = list(range(n))
+        keys = list(range(m))
+    keys = [k for k in keys if k < n]                            # F:1379-1385
     return [{"at": int((stamps[k] / fps) * 1000), "pos": 100 - int(round(norm[k]))} for k in keys]   # F:1378-1382

@@ -32,6 +32,9 @@ CASES = [
     {"name": "vr", "fps": 30.0, "n_frames": 90, "settings": {"vr_mode": True, "pov_mode": False, "keyframe_reduction": True}},
     {"name": "pov_60fps", "fps": 60.0, "n_frames": 150, "settings": {"vr_mode": False, "pov_mode": True, "keyframe_reduction": False}},
     {"name": "vr_pov", "fps": 30.0, "n_frames": 60, "settings": {"vr_mode": True, "pov_mode": True, "keyframe_reduction": True}},
+    # 4 frames = 3 pairs: shorter than the 5-tap smoother, the reference keeps going on np.convolve's 5 samples,
+    # drops the indices without a time stamp and returns error_occurred = True (F:1383-1385)
+    {"name": "short_4_frames", "fps": 30.0, "n_frames": 4, "settings": {"vr_mode": False, "pov_mode": True, "keyframe_reduction": False}},
 ]
 
 
@@ -52,7 +55,8 @@ def main():
                 vw.write(cv2.cvtColor(f, cv2.COLOR_GRAY2BGR))
             vw.release()
             logs = []
-            assert not ref.process_video(path, settings, logs.append), logs
+            err = bool(ref.process_video(path, settings, logs.append))
+            assert err == (case["n_frames"] < 6), logs
             acts = json.load(open(os.path.join(td, "clip.funscript")))["actions"]
         gap = None
         if not settings["pov_mode"]:      # the argmax only matters without the POV shortcut
@@ -69,7 +73,7 @@ def main():
                 assert (m1[0], m1[1]) == (m2[0], m2[1]) and min(m1[3], m2[3]) >= 1e-3, (case["name"], m1, m2)
                 gap = min(gap, m1[3], m2[3])
         out["cases"].append({"name": case["name"], "fps": case["fps"], "spec": spec, "settings": settings, "actions": acts,
-                             "min_argmax_gap": gap})
+                             "min_argmax_gap": gap, "error_occurred": err})
         print(case["name"], len(acts), "actions", "min argmax gap", gap)
     json.dump(out, open(os.path.join(HERE, "video_modes.json"), "w"))
 

@@ -159,3 +159,37 @@ def test_oracle_pipeline_vs_golden_video_modes(golden_dir):
         vals, cuts, _ = mo.process_bracket(gray, st)
         acts = mo.postprocess([(float(vals[j]), bool(cuts[j]), idx[j]) for j in range(len(vals))], case["fps"], st)
         assert acts == case["actions"], case["name"]
+
+
+def test_postproc_product_equals_oracle_on_random_series():
+    """Row N1 beyond the five golden cases: 60 random series (lengths 2..500, random cut positions incl. adjacent
+    cuts and cuts at both ends, 24..120 fps containers, both keyframe modes, short and long windows) through the
+    shipped post-processing and through the oracle restatement -- and through the reference's own statements
+    when /root/reference exists (build container)."""
+    from funscript_flow_b200 import postproc
+    rng = np.random.default_rng(11)
+    pp = ref_loader.postproc_function(ref_loader.load("ffref_pp", serial_pools=True)) if ref_loader.available() else None
+    for case in range(60):
+        n = int(rng.choice([2, 3, 4, 5, 7, 12, 40, 150, 500]))
+        fps = float(rng.choice([23.976, 24.0, 25.0, 29.97, 30.0, 50.0, 59.94, 60.0, 120.0]))
+        step = max(1, int(np.ceil(fps / 30.0)))
+        kind = case % 3
+        if kind == 0:
+            vals = rng.standard_normal(n).cumsum() * 0.2
+        elif kind == 1:
+            vals = np.sin(np.arange(n) * rng.uniform(0.05, 0.9)) * rng.uniform(0.1, 6) + rng.standard_normal(n) * 0.05
+        else:
+            vals = np.zeros(n) if case % 2 else np.full(n, 0.37)          # flat series: the normalisation's degenerate case
+        cuts = rng.random(n) < rng.choice([0.0, 0.02, 0.2])
+        if n > 3 and case % 5 == 0:
+            cuts[0] = cuts[-1] = True
+            cuts[1] = True
+        idx = [i * step for i in range(n)]
+        prm = {"detrend_window": float(rng.choice([0.5, 1.5, 2.0, 5.0])), "norm_window": float(rng.choice([1.0, 3.0, 4.0, 10.0])),
+               "keyframe_reduction": bool(case % 2)}
+        ffl = [(float(vals[i]), bool(cuts[i]), idx[i]) for i in range(n)]
+        want = mo.postprocess(ffl, fps, prm)
+        got = postproc.scalars_to_actions(vals.tolist(), cuts.tolist(), idx, fps, prm)
+        assert got == want, (case, n, fps, prm)
+        if pp is not None:
+            assert pp(ffl, fps, fps / step, prm, lambda *_: None) == want, (case, n, fps, prm)
