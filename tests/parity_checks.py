@@ -138,6 +138,41 @@ def check_reductions_kat(ctx, golden_dir):
     assert [x, y] == exp["max_divergence"][:2]
 
 
+def check_reductions_random(ctx, n_cases=24, max_side=97, seed=123):
+    """Device reductions against the oracle on random flow fields of random (odd, non-square) sizes: integer centres
+    on a pixel column / row (the `x == cx` branch), fractional centres, centres on the border and outside the frame,
+    POV mode, a constant field (all |div| == 0: the first pixel wins), duplicated maxima (first in C order wins)."""
+    from oracle import motion_np as mo
+    rng = np.random.default_rng(seed)
+    for case in range(n_cases):
+        w, h = int(rng.integers(16, max_side)), int(rng.integers(16, max_side))
+        kind = case % 4
+        if kind == 0:
+            flow = rng.standard_normal((h, w, 2)).astype(np.float32)
+        elif kind == 1:
+            flow = (rng.standard_normal((h, w, 2)) * 8).astype(np.float32).round()      # many exact ties
+        elif kind == 2:
+            flow = np.full((h, w, 2), np.float32(rng.uniform(-2, 2)), np.float32)       # zero divergence everywhere
+        else:   # the left half repeated on the right: every interior maximum exists twice, the first in C order wins
+            flow = rng.standard_normal((h, w, 2)).astype(np.float32)
+            flow[:, w // 2: 2 * (w // 2)] = flow[:, : w // 2]
+        x, y, v = ctx.max_divergence(flow)
+        rx, ry, rv = mo.max_divergence(flow)
+        assert (x, y) == (int(rx), int(ry)), (case, w, h, (x, y), (rx, ry))
+        assert np.float32(v) == np.float32(rv), (case, v, rv)
+        mm = ctx.mean_magnitude(flow) if hasattr(ctx, "mean_magnitude") else None
+        if mm is not None:
+            ref_mm = mo.mean_magnitude(flow)
+            assert abs(mm - ref_mm) <= 1e-6 * max(1.0, abs(ref_mm)), (case, mm, ref_mm)
+        centres = [[float(rng.integers(0, w)), float(rng.integers(0, h))], [rng.uniform(0, w - 1), rng.uniform(0, h - 1)],
+                   [0.0, 0.0], [float(w - 1), float(h - 1)], [-3.5, h + 2.25], [w / 2, h - 1]]
+        for c in centres:
+            for pov in (False, True):
+                got = ctx.radial_motion(flow, c, False, pov)
+                ref = mo.radial_motion_weighted(flow, c, False, pov)
+                assert abs(got - ref) <= 1e-6 * max(1.0, abs(ref)) + 1e-9, (case, w, h, c, pov, got, ref)
+
+
 def check_golden_pairs(ctx, golden_dir, names=("a", "b", "c")):
     """precompute_flow_info() outputs recorded from the reference (cv2 Farneback + NumPy)."""
     g = np.load(os.path.join(golden_dir, "pairs.npz"))

@@ -26,6 +26,10 @@ def test_reduction_known_answers(emu_ctx, golden_dir):
     pc.check_reductions_kat(emu_ctx, golden_dir)
 
 
+def test_reductions_random_fields(emu_ctx):
+    pc.check_reductions_random(emu_ctx, n_cases=12, max_side=64)
+
+
 def test_golden_pairs(emu_ctx, golden_dir):
     pc.check_golden_pairs(emu_ctx, golden_dir, names=("b", "c"))
 

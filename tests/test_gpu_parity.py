@@ -37,6 +37,10 @@ def test_reduction_known_answers(gpu_ctx, golden_dir):
     pc.check_reductions_kat(gpu_ctx, golden_dir)
 
 
+def test_reductions_random_fields(gpu_ctx):
+    pc.check_reductions_random(gpu_ctx, n_cases=40, max_side=300)
+
+
 def test_golden_pairs(gpu_ctx, golden_dir):
     pc.check_golden_pairs(gpu_ctx, golden_dir)
 

@@ -193,3 +193,24 @@ def test_postproc_product_equals_oracle_on_random_series():
         assert got == want, (case, n, fps, prm)
         if pp is not None:
             assert pp(ffl, fps, fps / step, prm, lambda *_: None) == want, (case, n, fps, prm)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference only exists in the build container")
+def test_motion_oracle_equals_live_reference_on_random_fields():
+    """The restated max_divergence / radial_motion_weighted against the reference's own functions on the field
+    families of parity_checks.check_reductions_random (ties, zero divergence, centres on and off the frame)."""
+    ref = ref_loader.load("ffref_rand", serial_pools=True)
+    rng = np.random.default_rng(123)
+    for case in range(30):
+        w, h = int(rng.integers(2, 80)), int(rng.integers(2, 80))
+        flow = rng.standard_normal((h, w, 2)).astype(np.float32)
+        if case % 3 == 1:
+            flow = (flow * 8).round()
+        elif case % 3 == 2:
+            flow[:] = np.float32(rng.uniform(-2, 2))
+        a, b = ref.max_divergence(flow), mo.max_divergence(flow)
+        assert (int(a[0]), int(a[1])) == (int(b[0]), int(b[1])) and np.float32(a[2]) == np.float32(b[2])
+        for c in ([float(rng.integers(0, w)), float(rng.integers(0, h))], [rng.uniform(0, w), rng.uniform(0, h)], [-3.5, h + 2.25]):
+            for pov in (False, True):
+                assert ref.radial_motion_weighted(flow, c, False, pov) == mo.radial_motion_weighted(flow, c, False, pov)
+        assert ref.radial_motion_weighted(flow, [1.0, 1.0], True, False) == mo.radial_motion_weighted(flow, [1.0, 1.0], True, False) == 0.0
