@@ -7,6 +7,7 @@ import subprocess
 import sys
 
 import numpy as np
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -120,3 +121,37 @@ def test_numa_binding_reads_sysfs(tmp_path, emu_lib, monkeypatch):
     lib = _native.load(emu_lib)
     monkeypatch.undo()
     assert _native.device_pci_bus_id(0, lib_path=emu_lib) == "0000:00:00.0"
+
+
+def test_parallel_decode_returns_the_same_frames(tmp_path):
+    """The multi-handle reader (spans decoded on their own VideoCapture, handed out in order) yields exactly the
+    frames of the sequential reader -- on intra-only containers and on one with inter-coded frames (mp4v), with
+    step-2 sampling, and it falls back to the sequential reader when a seek is inexact."""
+    cv2 = pytest.importorskip("cv2")
+    from funscript_flow_b200 import runner
+    from funscript_flow_b200.synth import make_clip
+    clip = make_clip(96, 64, 90, seed=5, period=11.0, amplitude=0.3)
+    tried = 0
+    for codec, ext in (("FFV1", "avi"), ("MJPG", "avi"), ("mp4v", "mp4")):
+        path = str(tmp_path / f"c_{codec}.{ext}")
+        vw = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*codec), 30.0, (96, 64), True)
+        if not vw.isOpened():
+            continue
+        for f in clip:
+            vw.write(cv2.cvtColor(f, cv2.COLOR_GRAY2BGR))
+        vw.release()
+        tried += 1
+        for idx in (list(range(90)), list(range(0, 90, 2)), list(range(3, 90, 7))):
+            seq = list(runner.iter_sampled_bgr(path, idx))
+            par = list(runner.iter_sampled_bgr_parallel(path, idx, workers=3, span=8))
+            assert len(seq) == len(par) == len(idx)
+            assert all(np.array_equal(a, b) for a, b in zip(seq, par)), (codec, idx[:3])
+    assert tried > 0
+    # inexact seek -> sequential fallback, same frames
+    real = runner._decode_span
+    runner._decode_span = lambda p, w, s: (real(p, w, s)[0], w[0] < 16)
+    try:
+        par = list(runner.iter_sampled_bgr_parallel(path, list(range(90)), workers=3, span=8))
+    finally:
+        runner._decode_span = real
+    assert all(np.array_equal(a, b) for a, b in zip(runner.iter_sampled_bgr(path, list(range(90))), par)) and len(par) == 90
