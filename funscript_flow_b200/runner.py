@@ -409,8 +409,10 @@ def run_headless(input_path: str, settings: Dict, log_func: Optional[Callable[[s
     errors = 0
     for i, v in enumerate(vids):
         log_func(f"Processing file {i + 1}/{len(vids)}: {v}")
-        errors += bool(process_video(v, settings, log_func, progress_callback=None))
+        progress = (lambda prog: print(f"Video progress: {prog}%")) if logf else None      # F:2634
+        errors += bool(process_video(v, settings, log_func, progress_callback=progress))
     log_func("Batch processing complete.")
     if logf:
         logf.close()
+        print(f"Done. See {logf.name} for details.")                                         # F:2637
     return errors
