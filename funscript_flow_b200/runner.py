@@ -305,6 +305,18 @@ def process_video(video_path, params, log_func, progress_callback=None, cancel_f
         log_func(f"Skipping: output file exists ({output_path})")
         return False
     log_func(f"Processing video: {video_path}")
+    try:      # F:1114-1131: properties first, so the two header lines precede the work as in the reference
+        import cv2
+        cap = cv2.VideoCapture(video_path)
+        if not cap.isOpened():
+            raise IOError("cannot open the container")
+        total, fps0 = int(cap.get(cv2.CAP_PROP_FRAME_COUNT)), float(cap.get(cv2.CAP_PROP_FPS))
+        cap.release()
+        step0 = postproc.sampling_step(fps0)
+        log_func(f"FPS: {fps0:.2f}; downsampled to ~{fps0 / step0:.2f} fps; {len(range(0, total, step0))} frames selected.")
+    except Exception as exc:
+        log_func(f"ERROR: Unable to open video at {video_path}: {exc}")
+        return True
     log_func("Using backend: B200 (sm_100a)")
     try:
         res = process_video_series(video_path, params, progress_callback=progress_callback, cancel_flag=cancel_flag)
@@ -315,8 +327,6 @@ def process_video(video_path, params, log_func, progress_callback=None, cancel_f
         log_func("User bailed.")
         return False
     values, cuts, stamps, fps = res
-    step = postproc.sampling_step(fps)
-    log_func(f"FPS: {fps:.2f}; downsampled to ~{fps / step:.2f} fps; {len(stamps) + 1} frames selected.")
     errors: List[str] = []
     actions = postproc.scalars_to_actions(values, cuts, stamps, fps, params, errors) if values else []
     for msg in errors:           # F:1383-1385: series shorter than the smoother (fewer than 6 sampled frames)
@@ -405,10 +415,10 @@ def run_headless(input_path: str, settings: Dict, log_func: Optional[Callable[[s
     if not vids:
         log_func("No video files found.")
     else:
-        log_func(f"Found {len(vids)} video file(s)" + (f" for rank {rank}/{world}" if world > 1 else ""))
+        log_func(f"Found {len(vids)} file(s)." + (f" (rank {rank} of {world})" if world > 1 else ""))      # F:376
     errors = 0
     for i, v in enumerate(vids):
-        log_func(f"Processing file {i + 1}/{len(vids)}: {v}")
+        log_func(f"--- Processing file {i + 1}/{len(vids)}: {v} ---")                                       # F:377
         progress = (lambda prog: print(f"Video progress: {prog}%")) if logf else None      # F:2634
         errors += bool(process_video(v, settings, log_func, progress_callback=progress))
     log_func("Batch processing complete.")
