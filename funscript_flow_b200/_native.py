@@ -43,6 +43,7 @@ def load(path: Optional[str] = None) -> C.CDLL:
         "ffb_version": (i32, []),
         "ffb_device_count": (i32, [i32p]),
         "ffb_device_pci_bus_id": (i32, [i32, C.c_char_p, i32]),
+        "ffb_device_name": (i32, [i32, C.c_char_p, i32]),
         "ffb_last_error": (C.c_char_p, [vp]),
         "ffb_create": (i32, [i32, C.POINTER(vp)]),
         "ffb_destroy": (None, [vp]),
@@ -100,6 +101,13 @@ def device_pci_bus_id(device: int = 0, lib_path: Optional[str] = None) -> Option
     if load(lib_path).ffb_device_pci_bus_id(int(device), buf, 32) != 0:
         return None
     return buf.value.decode().lower()
+
+
+def device_name(device: int = 0, lib_path: Optional[str] = None) -> Optional[str]:
+    buf = C.create_string_buffer(256)
+    if load(lib_path).ffb_device_name(int(device), buf, 256) != 0:
+        return None
+    return buf.value.decode()
 
 
 def level_plan(width: int, height: int, lib_path: Optional[str] = None):

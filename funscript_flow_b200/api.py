@@ -77,6 +77,20 @@ def get_available_backends() -> Dict[str, bool]:
     return {"CPU": False, "CUDA": n > 0, "OpenCL": False, "DNN": False}
 
 
+def get_gpu_info() -> str:
+    """F:64-99: "CUDA: <device name>" for one GPU, "CUDA: <n> devices" for several, "CPU only" when there is none
+    (the reference's wording for 'no accelerator'; this build cannot run in that case)."""
+    try:
+        n = _native.device_count()
+    except Exception:
+        n = 0
+    if n <= 0:
+        return "CPU only"
+    if n == 1:
+        return f"CUDA: {_native.device_name(0) or 'Device 0'}"
+    return f"CUDA: {n} devices"
+
+
 def _as_frames(frames) -> np.ndarray:
     if isinstance(frames, np.ndarray) and frames.ndim == 3:
         arr = frames

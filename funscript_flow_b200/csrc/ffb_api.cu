@@ -1123,6 +1123,14 @@ int ffb_device_pci_bus_id(int device, char* buf, int buf_len) {
     return FFB_OK;
 }
 
+int ffb_device_name(int device, char* buf, int buf_len) {
+    if (!buf || buf_len < 2) return FFB_E_INVALID;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { cudaGetLastError(); buf[0] = 0; return FFB_E_NODEVICE; }
+    snprintf(buf, (size_t)buf_len, "%s", prop.name);
+    return FFB_OK;
+}
+
 const char* ffb_last_error(const ffb_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
 
 int ffb_create(int device, ffb_ctx** out) {

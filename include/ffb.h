@@ -46,6 +46,8 @@ int  ffb_device_count(int* n_devices);
 /* PCI bus id ("0000:1b:00.0") of a device, for placing the host process (and so its pinned staging
  * buffers) on the NUMA node the GPU hangs off; no context needed. */
 int  ffb_device_pci_bus_id(int device, char* buf, int buf_len);
+/* Marketing name of a device ("NVIDIA B200"), what the reference shows through cv2.cuda.getDeviceName (F:77). */
+int  ffb_device_name(int device, char* buf, int buf_len);
 const char* ffb_last_error(const ffb_ctx* ctx /* NULL = last error of ffb_create */);
 
 int  ffb_create(int device, ffb_ctx** out_ctx);

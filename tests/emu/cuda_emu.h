@@ -282,6 +282,8 @@ static inline const char* cudaGetErrorString(cudaError_t e) { return e == 0 ? "n
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+struct cudaDeviceProp { char name[256]; };
+static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { snprintf(p->name, sizeof(p->name), "emulated device"); return cudaSuccess; }
 static inline cudaError_t cudaDeviceGetPCIBusId(char* buf, int len, int) { snprintf(buf, len, "0000:00:00.0"); return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }

@@ -73,3 +73,15 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "libffb_emu" not in src and "cuda_emu.h" not in src.replace('#include "cuda_emu.h"', ""), f
+
+
+def test_gpu_info_strings_without_a_gpu():
+    """get_gpu_info mirrors F:64-99; on a box without a device it says what the reference says ("CPU only") and
+    get_available_backends reports CUDA False -- nothing pretends to be runnable."""
+    from funscript_flow_b200 import api
+    if _native.device_count() == 0:
+        assert api.get_gpu_info() == "CPU only"
+        assert api.get_available_backends() == {"CPU": False, "CUDA": False, "OpenCL": False, "DNN": False}
+        assert _native.device_name(0) is None and _native.device_pci_bus_id(0) is None
+    else:
+        assert api.get_gpu_info().startswith("CUDA: ")
