@@ -85,3 +85,41 @@ def test_gpu_info_strings_without_a_gpu():
         assert _native.device_name(0) is None and _native.device_pci_bus_id(0) is None
     else:
         assert api.get_gpu_info().startswith("CUDA: ")
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/ffb.h compiles as C11 with -Wall -Werror -pedantic (no C++ leaking into the boundary) and a C program
+    that calls the device-independent entry points links against libffb.so and runs without a GPU."""
+    import shutil
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = build.build()
+    src = tmp_path / "use_ffb.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "ffb.h"
+int main(void) {
+    int n = -1;
+    ffb_ctx* ctx = NULL;
+    int w[4], h[4], ks[4];
+    double sg[4];
+    int levels = 0;
+    if (ffb_version() != FFB_VERSION) return 1;
+    if (ffb_device_count(&n) != FFB_OK || n < 0) return 2;
+    if (ffb_level_plan(1920, 1080, &levels, w, h, ks, sg) != FFB_OK || levels != 4 || w[0] != 240 || w[3] != 1920) return 3;
+    if (n == 0 && ffb_create(0, &ctx) != FFB_E_NODEVICE) return 4;      /* no CPU fallback */
+    if (n == 0 && ffb_last_error(NULL)[0] == 0) return 5;
+    if (ctx) ffb_destroy(ctx);
+    printf("ok %d devices, %s\n", n, ffb_kernel_name(FFB_K_FLOW_ITER));
+    return 0;
+}
+''')
+    exe = tmp_path / "use_ffb"
+    cmd = [gcc, "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(root, "include"), str(src), "-o", str(exe),
+           lib, "-Wl,-rpath," + os.path.dirname(lib)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0 and run.stdout.startswith("ok "), (run.returncode, run.stdout, run.stderr)
