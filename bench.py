@@ -141,7 +141,9 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000 * total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"C2: synthetic {args.width}x{args.height} 30 fps clip window", "pairs_per_step": sample},
+            "config": {"workload": f"C2: synthetic {args.width}x{args.height} 30 fps clip, window of {args.pairs_per_step + 1} frames per step per GPU",
+                       "pairs_per_step": args.pairs_per_step, "sample_pairs_per_step": sample, "levels": 4, "iterations": 3,
+                       "note": "each step is a bounded sample (the first sample_pairs_per_step pairs) of the GPU arm's step"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{sample} pairs/step x {args.steps} steps, cv2 {cv2.__version__} Farneback + NumPy via "
                                        f"multiprocessing.Pool({cores}) as F:1190-1236"},
