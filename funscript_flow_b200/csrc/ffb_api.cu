@@ -544,12 +544,12 @@ int launch_flow_iter_t(ffb_ctx* c, FfbIterArgs a, int npairs, int sh_target, dou
     // at most sh_target rows per segment, at least min_seg segments per level (coarse levels would
     // otherwise be a handful of long, latency-bound marches), never under 32 rows
     static const int min_seg_env = getenv("FFB_ITER_MINSEG") ? atoi(getenv("FFB_ITER_MINSEG")) : 0;
-    // frames of 1280x720 and more: 4 segments on every level (parallelism for their 64-pair batches); smaller frames
-    // come in batches of hundreds, and every segment pays 14 halo rows: 2 (+7 % at 256x256, +3.5 % at 640x360;
-    // at 1080p 2 segments on the coarse levels lose 0.5 %: profiles/r1_sweep_segments.txt).  The rule looks at the
-    // frame the context is configured for, never at the batch.
+    // frames of 1280x720 and more: at least 3 segments on every level (parallelism for their 64-pair batches; 3 beats 4
+    // by 0.5 % and 2 loses 0.5 % at 1080p); smaller frames come in batches of hundreds, and every segment pays 14 halo
+    // rows: 2 (+7 % at 256x256, +3.5 % at 640x360) -- profiles/r1_sweep_segments.txt.  The rule looks at the frame
+    // the context is configured for, never at the batch.
     const long long frame_px = c->seg_frame_px > 0 ? c->seg_frame_px : (long long)w * h;      // stage hooks: the level itself
-    const int min_seg = min_seg_env > 0 ? min_seg_env : (frame_px >= 1280LL * 720 ? 4 : 2);
+    const int min_seg = min_seg_env > 0 ? min_seg_env : (frame_px >= 1280LL * 720 ? 3 : 2);
     int nseg = (h + sh_target - 1) / sh_target;
     if (nseg < min_seg) nseg = min_seg;
     if (nseg > (h + 31) / 32) nseg = (h + 31) / 32;
