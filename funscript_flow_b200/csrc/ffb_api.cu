@@ -611,7 +611,18 @@ int launch_flow_iter(ffb_ctx* c, FfbRing R, size_t plane, int rp, int w, int h, 
         case 12827: return launch_flow_iter_t<128, 2, 4, true, 8>(c, a, npairs, k.sh, bytes);    // hfirst, 8 outputs / task
         case 12828:   // "x8": hfirst + 2-CTA clusters sharing the seam columns through DSMEM
             return launch_flow_iter_t<128, 2, 4, true, 4, true>(c, a, npairs, k.sh, bytes);
+        case 16026:   // 160-thread strips (144 outputs): 256- and 128-column levels split into 2 / 1 strips instead of
+                      // 3 / 2 (the 256x256 product mode); 3 CTAs / SM.  Not measured yet (round 2).
+            return launch_flow_iter_t<160, 2, 3, true>(c, a, npairs, k.sh, bytes);
         default: break;
+    }
+    // Frames under 1280x720 (the reference's 256x256 product mode, 640x360): 160-thread strips of up to 144 outputs, so a
+    // 256-column level is 2 strips instead of 3 and a 128-column level 1 instead of 2: +10 % at 256x256; at 1080p the
+    // same variant loses 3 % (3 CTAs / SM), so large frames keep 128 threads (profiles/r1_sweep_segments.txt).
+    {
+        const long long frame_px = c->seg_frame_px > 0 ? c->seg_frame_px : (long long)w * h;
+        if (key == 12826 && tx == 0 && frame_px < 1280LL * 720)
+            return launch_flow_iter_t<160, 2, 3, true>(c, a, npairs, k.sh, bytes);
     }
     // default: 128 threads x 2 rows per step, horizontal phase first; TX = loads moved to the texture pipe
     switch (tx) {

@@ -177,6 +177,45 @@ def test_cluster_variant_in_subprocess(emu_lib):
     assert res.returncode == 0, res.stdout + res.stderr
 
 
+def test_large_frame_variant_in_subprocess(emu_lib, golden_dir):
+    """Frames under 1280x720 run the 160-thread strips, so the small frames of this CPU suite would never reach the
+    128-thread kernel that 1080p and 4K use: FFB_ITER_CFG=128x2x5 forces it (the GPU suite covers it at full size)."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from funscript_flow_b200 import _native\n"
+        "import parity_checks as pc\n"
+        "ctx = _native.FlowContext(0, %r)\n"
+        "print(pc.check_farneback_vs_cv2(ctx, 333, 217))\n"
+        "pc.check_batch_independence(ctx, 300, 72, n_frames=6)\n"
+        "pc.check_golden_bracket(ctx, %r)\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)), emu_lib, golden_dir)
+    env = dict(os.environ, FFB_ITER_CFG="128x2x5")
+    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout + res.stderr
+
+
+def test_wide_strip_variant_in_subprocess(emu_lib):
+    """The 160-thread strip variant forced on any frame size (FFB_ITER_CFG=160x2x6: 144 output columns per CTA; the
+    default for frames under 1280x720)."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from funscript_flow_b200 import _native\n"
+        "import parity_checks as pc\n"
+        "ctx = _native.FlowContext(0, %r)\n"
+        "print(pc.check_farneback_vs_cv2(ctx, 256, 256))\n"
+        "pc.check_batch_independence(ctx, 300, 72, n_frames=6)\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)), emu_lib)
+    env = dict(os.environ, FFB_ITER_CFG="160x2x6")
+    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout + res.stderr
+
+
 def test_error_paths_and_strided_input(emu_ctx):
     """Host logic of the C ABI: calls out of sequence and out-of-range requests fail with the documented
     codes (no exceptions swallowed, no fallback); frames given as a strided view (pitch > width) are
