@@ -614,6 +614,8 @@ int launch_flow_iter(ffb_ctx* c, FfbRing R, size_t plane, int rp, int w, int h, 
         case 16026:   // 160-thread strips (144 outputs): 256- and 128-column levels split into 2 / 1 strips instead of
                       // 3 / 2 (the 256x256 product mode); 3 CTAs / SM.  Not measured yet (round 2).
             return launch_flow_iter_t<160, 2, 3, true>(c, a, npairs, k.sh, bytes);
+        case 9626:    // 96-thread strips (80 outputs), 5 CTAs / SM: candidate for levels under 128 columns (not measured yet)
+            return launch_flow_iter_t<96, 2, 5, true>(c, a, npairs, k.sh, bytes);
         default: break;
     }
     // Frames under 1280x720 (the reference's 256x256 product mode, 640x360): 160-thread strips of up to 144 outputs, so a

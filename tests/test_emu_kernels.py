@@ -197,9 +197,10 @@ def test_large_frame_variant_in_subprocess(emu_lib, golden_dir):
     assert res.returncode == 0, res.stdout + res.stderr
 
 
-def test_wide_strip_variant_in_subprocess(emu_lib):
-    """The 160-thread strip variant forced on any frame size (FFB_ITER_CFG=160x2x6: 144 output columns per CTA; the
-    default for frames under 1280x720)."""
+@pytest.mark.parametrize("cfg", ["160x2x6", "96x2x6"])
+def test_wide_strip_variant_in_subprocess(emu_lib, cfg):
+    """Strip widths forced on any frame size: FFB_ITER_CFG=160x2x6 (144 output columns per CTA; the default for frames
+    under 1280x720) and 96x2x6 (80 columns; prepared for the levels under 128 columns, not measured yet)."""
     import os
     import subprocess
     import sys
@@ -211,7 +212,7 @@ def test_wide_strip_variant_in_subprocess(emu_lib):
         "print(pc.check_farneback_vs_cv2(ctx, 256, 256))\n"
         "pc.check_batch_independence(ctx, 300, 72, n_frames=6)\n"
     ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)), emu_lib)
-    env = dict(os.environ, FFB_ITER_CFG="160x2x6")
+    env = dict(os.environ, FFB_ITER_CFG=cfg)
     res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout + res.stderr
 
