@@ -197,10 +197,6 @@ struct ffb_ctx {
     Level lev[FFB_MAX_LEVELS];
     float* R = nullptr;
     size_t r_slot_floats = 0;
-    // texture views of the expansion ring (one float4 view + one float view per element), see TX in k_flow_iter
-    std::vector<cudaTextureObject_t> h_tex4, h_tex1;
-    cudaTextureObject_t *d_tex4 = nullptr, *d_tex1 = nullptr;
-    int iter_tex = 0;      // TX variant used by the bracket path (0 = LSU loads only)
     long long seg_frame_px = 0;      // pixels of the frame whose levels are being iterated (segmentation rule)
     float2* ring = nullptr;
     size_t ring_stride = 0;   // float2 per ring element
@@ -443,107 +439,48 @@ int launch_upsample(ffb_ctx* c, const float2* src, size_t src_stride, int sp, in
     return FFB_OK;
 }
 
-// Tunables of the fused iteration kernel (threads per CTA x rows per step, rows per segment).
-// Defaults are compiled in; FFB_ITER_CFG=NTxU and FFB_ITER_SH=rows override them for tuning runs.
-#ifndef FFB_ITER_TEX_DEFAULT
-#define FFB_ITER_TEX_DEFAULT 0
-#endif
-struct IterCfg { int nt, u, minb, sh; };
-IterCfg iter_cfg() {
-    static IterCfg cfg = [] {
-        IterCfg c{128, 2, 6, 270};
-        if (const char* e = getenv("FFB_ITER_CFG")) {
-            int nt = 0, u = 0, m = 0;
-            const int got = sscanf(e, "%dx%dx%d", &nt, &u, &m);
-            if (got >= 2) { c.nt = nt; c.u = u; c.minb = got == 3 ? m : 0; }
-        }
-        if (const char* e = getenv("FFB_ITER_SH")) { const int v = atoi(e); if (v >= 16) c.sh = v; }
-        return c;
-    }();
-    return cfg;
-}
-
-// Linear-memory texture object over `bytes` at `ptr` with float4 or float texels.
-int make_linear_texture(ffb_ctx* c, const void* ptr, size_t bytes, bool vec4, cudaTextureObject_t* out) {
-#ifdef FFB_EMU
-    (void)c; (void)bytes; (void)vec4;
-    *out = (cudaTextureObject_t)(uintptr_t)ptr;      // tests/emu: tex1Dfetch indexes the pointer
-#else
-    cudaResourceDesc rd = {};
-    cudaTextureDesc td = {};
-    rd.resType = cudaResourceTypeLinear;
-    rd.res.linear.devPtr = const_cast<void*>(ptr);
-    rd.res.linear.desc = vec4 ? cudaCreateChannelDesc<float4>() : cudaCreateChannelDesc<float>();
-    rd.res.linear.sizeInBytes = bytes;
-    td.readMode = cudaReadModeElementType;
-    td.filterMode = cudaFilterModePoint;
-    td.addressMode[0] = cudaAddressModeClamp;
-    td.normalizedCoords = 0;
-    CK(c, cudaCreateTextureObject(out, &rd, &td, nullptr));
-#endif
-    return FFB_OK;
-}
-
-void free_textures(ffb_ctx* c) {
-    for (cudaTextureObject_t t : c->h_tex4) cudaDestroyTextureObject(t);
-    for (cudaTextureObject_t t : c->h_tex1) cudaDestroyTextureObject(t);
-    c->h_tex4.clear(); c->h_tex1.clear();
-    dev_free(c->d_tex4); dev_free(c->d_tex1);
-    c->iter_tex = 0;
-}
-
-// Texture views of the S elements of the expansion ring.  Skipped (LSU loads only) when an element
-// exceeds the device's linear-texture width.
-int make_ring_textures(ffb_ctx* c) {
-    free_textures(c);
-    static const int want = getenv("FFB_ITER_TEX") ? atoi(getenv("FFB_ITER_TEX")) : FFB_ITER_TEX_DEFAULT;
-    if (want <= 0 || want > 4) return FFB_OK;
-    size_t max_texels = (size_t)1 << 27;
-#ifndef FFB_EMU
-    int v = 0;
-    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxTexture1DLinearWidth, c->device) == cudaSuccess && v > 0) max_texels = (size_t)v;
-#endif
-    if (c->r_slot_floats > max_texels) return FFB_OK;
-    for (int s = 0; s < c->S; ++s) {
-        cudaTextureObject_t t4 = 0, t1 = 0;
-        const float* base = c->R + (size_t)s * c->r_slot_floats;
-        TRY(make_linear_texture(c, base, c->r_slot_floats * sizeof(float), true, &t4));
-        c->h_tex4.push_back(t4);
-        TRY(make_linear_texture(c, base, c->r_slot_floats * sizeof(float), false, &t1));
-        c->h_tex1.push_back(t1);
+// Tunables of the fused iteration kernel.  The defaults are compiled in; the environment overrides exist for
+// tuning runs and for the tests that force a variant onto small frames:
+//   FFB_ITER_CFG=NTxUxHO   threads per CTA (= matrix columns per strip) x rows per step x outputs per horizontal task
+//   FFB_ITER_CFG_COARSE    same, for the levels k >= 2 only
+//   FFB_ITER_OPT           bit 0: non-allocating loads of R0 / flow-in, bit 1: bulk L2 prefetch (128x2x4 only)
+//   FFB_ITER_SH / FFB_ITER_MINSEG   rows per march segment (upper bound) / minimum segments per level
+//   FFB_ITER_SWMAX=0       equal-width strips (round 1) instead of full-width strips plus a narrow last one
+struct IterCfg { int nt, u, ho, sh, opt, swmax; int cnt, cu, cho; };
+IterCfg iter_cfg() {      // parsed per launch (a few getenv calls): tuning runs switch variants inside one process
+    IterCfg c{0, 2, 4, 270, 0, 1, 0, 2, 4};
+    if (const char* e = getenv("FFB_ITER_CFG")) {
+        int nt = 0, u = 0, ho = 0;
+        if (sscanf(e, "%dx%dx%d", &nt, &u, &ho) == 3) { c.nt = nt; c.u = u; c.ho = ho; }
     }
-    TRY(upload_vec(c, &c->d_tex4, c->h_tex4));
-    TRY(upload_vec(c, &c->d_tex1, c->h_tex1));
-    c->iter_tex = want;
-    return FFB_OK;
+    if (const char* e = getenv("FFB_ITER_CFG_COARSE")) {
+        int nt = 0, u = 0, ho = 0;
+        if (sscanf(e, "%dx%dx%d", &nt, &u, &ho) == 3) { c.cnt = nt; c.cu = u; c.cho = ho; }
+    }
+    if (const char* e = getenv("FFB_ITER_SH")) { const int v = atoi(e); if (v >= 16) c.sh = v; }
+    if (const char* e = getenv("FFB_ITER_OPT")) c.opt = atoi(e) & 3;
+    if (const char* e = getenv("FFB_ITER_SWMAX")) c.swmax = atoi(e) != 0;
+    return c;
 }
 
-template <int NT, int U, int MINB, bool HFIRST = false, int HO = 4, bool CL = false, int TX = 0>
+template <int NT, int U, int MINB, int HO = 4, int OPT = 0>
 int launch_flow_iter_t(ffb_ctx* c, FfbIterArgs a, int npairs, int sh_target, double bytes) {
     const int w = a.w, h = a.h;
-    int gx;
-    if (CL) {
-        // two CTAs per cluster: 2*NT matrix columns -> 2*SW outputs with SW <= NT - 7
-        const int sw_max = (NT - FFB_WIN_R) / HO * HO;
-        const int nclusters = (w + 2 * sw_max - 1) / (2 * sw_max);
-        a.SW = ffb_round_up((w + 2 * nclusters - 1) / (2 * nclusters), HO);
-        if (a.SW > sw_max) a.SW = sw_max;
-        gx = 2 * nclusters;
-        // the row buffer holds NT + 16 positions: the seam offset NT - SW must stay within 16 columns;
-        // widths that do not split into such clusters use the plain kernel
-        if (a.SW < NT - 16) return launch_flow_iter_t<NT, U, MINB, HFIRST, HO, false, TX>(c, a, npairs, sh_target, bytes);
+    const int sw_max = (NT - 2 * FFB_WIN_R) / HO * HO;
+    if (iter_cfg().swmax) {
+        // full-width strips; the last one is narrower and its idle warps skip the gather (k_flow_iter `live`)
+        a.SW = sw_max;
     } else {
-        const int sw_max = (NT - 2 * FFB_WIN_R) / HO * HO;
         const int nstrips = (w + sw_max - 1) / sw_max;
         a.SW = ffb_round_up((w + nstrips - 1) / nstrips, HO);
         if (a.SW > sw_max) a.SW = sw_max;
-        gx = (w + a.SW - 1) / a.SW;
     }
+    const int gx = (w + a.SW - 1) / a.SW;
     // Row segments depend on the level geometry only (never on the batch composition), so a pair's
     // result is bit-identical however frames are batched or sharded.
     // at most sh_target rows per segment, at least min_seg segments per level (coarse levels would
     // otherwise be a handful of long, latency-bound marches), never under 32 rows
-    static const int min_seg_env = getenv("FFB_ITER_MINSEG") ? atoi(getenv("FFB_ITER_MINSEG")) : 0;
+    const int min_seg_env = getenv("FFB_ITER_MINSEG") ? atoi(getenv("FFB_ITER_MINSEG")) : 0;
     // frames of 1280x720 and more: at least 3 segments on every level (parallelism for their 64-pair batches; 3 beats 4
     // by 0.5 % and 2 loses 0.5 % at 1080p); smaller frames come in batches of hundreds, and every segment pays 14 halo
     // rows: 2 (+7 % at 256x256, +3.5 % at 640x360) -- profiles/r1_sweep_segments.txt.  The rule looks at the frame
@@ -554,10 +491,10 @@ int launch_flow_iter_t(ffb_ctx* c, FfbIterArgs a, int npairs, int sh_target, dou
     if (nseg < min_seg) nseg = min_seg;
     if (nseg > (h + 31) / 32) nseg = (h + 31) / 32;
     if (nseg < 1) nseg = 1;
-    a.SH = ffb_round_up((h + nseg - 1) / nseg, 2);     // even: see the fused up-sampling in k_flow_iter
+    a.SH = ffb_round_up((h + nseg - 1) / nseg, U);     // even: see the fused up-sampling in k_flow_iter
     const int gy = (h + a.SH - 1) / a.SH;
-    auto kfn = a.up_src ? k_flow_iter<NT, U, MINB, HFIRST, true, HO, CL, TX> : k_flow_iter<NT, U, MINB, HFIRST, false, HO, CL, TX>;
-    const size_t smem = ffb_flow_iter_smem<NT, U, CL>();
+    auto kfn = a.up_src ? k_flow_iter<NT, U, MINB, true, HO, OPT> : k_flow_iter<NT, U, MINB, false, HO, OPT>;
+    const size_t smem = ffb_flow_iter_smem<NT, U, HO>();
     if (!c->attr_iter.count((const void*)kfn)) {
         CK(c, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         c->attr_iter.insert((const void*)kfn);
@@ -566,11 +503,7 @@ int launch_flow_iter_t(ffb_ctx* c, FfbIterArgs a, int npairs, int sh_target, dou
     // pair index varies fastest in launch order: the CTAs working on one spatial tile of consecutive
     // pairs are co-resident, so frame j+1's expansion (R1 of pair j, R0 of pair j+1) is read from
     // HBM once and hit in L2 the second time.
-    if (CL) {
-        FFB_LAUNCH_CLUSTER(kfn, dim3(npairs, gx, gy), dim3(NT), smem, c->launch_stream, 1, 2, 1, a);
-    } else {
-        FFB_LAUNCH(kfn, dim3(npairs, gx, gy), dim3(NT), smem, c->launch_stream, a);
-    }
+    FFB_LAUNCH(kfn, dim3(npairs, gx, gy), dim3(NT), smem, c->launch_stream, a);
     prof_end(c);
     CKL(c);
     return FFB_OK;
@@ -580,15 +513,10 @@ struct UpSrc {   // coarser-level flow to be up-sampled inside the iteration ker
     const float2* src = nullptr; size_t stride = 0; int sp = 0, wc = 0, hc = 0;
 };
 
-// tex_off >= 0: R is the context's expansion ring and tex_off the float offset of the level inside a ring
-// element, so the texture views may be used; -1 (stage hooks on scratch buffers): LSU loads only.
 int launch_flow_iter(ffb_ctx* c, FfbRing R, size_t plane, int rp, int w, int h, const float2* fin, size_t fin_stride,
-                     int fip, FfbRing fout, int fop, int npairs, const UpSrc* up = nullptr, long long tex_off = -1) {
+                     int fip, FfbRing fout, int fop, int npairs, const UpSrc* up = nullptr) {
     FfbIterArgs a;
     a.R = R; a.plane = (int)plane; a.rp = rp; a.w = w; a.h = h;
-    a.tex4 = c->d_tex4; a.tex1 = c->d_tex1; a.texA = a.texB = 0;
-    const int tx = (tex_off >= 0 && c->d_tex4) ? c->iter_tex : 0;
-    if (tx) { a.texA = (unsigned)(tex_off / 4); a.texB = (unsigned)(tex_off + 4 * (long long)plane); }
     a.fin = fin; a.fin_stride = fin_stride; a.fip = fip; a.fout = fout; a.fop = fop;
     a.SW = a.SH = 0;
     a.up_src = nullptr; a.up_stride = 0; a.usp = a.wc = a.hc = 0;
@@ -603,37 +531,35 @@ int launch_flow_iter(ffb_ctx* c, FfbRing R, size_t plane, int rp, int w, int h, 
     if (fop % 4 != 0 || ((uintptr_t)fout.base | (uintptr_t)fout.stride) % 32 != 0)
         return fail(c, FFB_E_INVALID, "flow output is not 32-byte aligned (pitch %d, stride %zu)", fop, fout.stride);
     const IterCfg k = iter_cfg();
-    // Variants kept after the round-1 sweeps (profiles/r1_sweep*.txt); the third number of FFB_ITER_CFG
-    // selects min blocks per SM, with 6 / 7 meaning "horizontal phase first" (/ 8 outputs per task).
-    const int key = k.nt * 100 + k.u * 10 + k.minb;
-    switch (key) {
-        case 12824: return launch_flow_iter_t<128, 2, 4>(c, a, npairs, k.sh, bytes);             // gather first, 4 CTAs/SM
-        case 12827: return launch_flow_iter_t<128, 2, 4, true, 8>(c, a, npairs, k.sh, bytes);    // hfirst, 8 outputs / task
-        case 12828:   // "x8": hfirst + 2-CTA clusters sharing the seam columns through DSMEM
-            return launch_flow_iter_t<128, 2, 4, true, 4, true>(c, a, npairs, k.sh, bytes);
-        case 16026:   // 160-thread strips (144 outputs): 256- and 128-column levels split into 2 / 1 strips instead of
-                      // 3 / 2 (the 256x256 product mode); 3 CTAs / SM.  Not measured yet (round 2).
-            return launch_flow_iter_t<160, 2, 3, true>(c, a, npairs, k.sh, bytes);
-        case 9626:    // 96-thread strips (80 outputs), 5 CTAs / SM: candidate for levels under 128 columns (not measured yet)
-            return launch_flow_iter_t<96, 2, 5, true>(c, a, npairs, k.sh, bytes);
+    int nt = k.nt, u = k.u, ho = k.ho;
+    if (k.cnt > 0 && c->cur_level >= 2) { nt = k.cnt; u = k.cu; ho = k.cho; }
+    if (nt == 0) {
+        // Frames under 1280x720 (the reference's 256x256 product mode, 640x360): 160-thread strips of up to 144 outputs, so a
+        // 256-column level is 2 strips instead of 3 and a 128-column level 1 instead of 2: +10 % at 256x256; at 1080p the
+        // same variant loses 3 % (3 CTAs / SM), so large frames keep 128 threads (profiles/r1_sweep_segments.txt).
+        const long long frame_px = c->seg_frame_px > 0 ? c->seg_frame_px : (long long)w * h;
+        nt = frame_px < 1280LL * 720 ? 160 : 128;
+    }
+    switch (nt * 100 + u * 10 + ho) {
+        case 12824:
+            switch (k.opt) {
+                case 1:  return launch_flow_iter_t<128, 2, 4, 4, 1>(c, a, npairs, k.sh, bytes);
+                case 2:  return launch_flow_iter_t<128, 2, 4, 4, 2>(c, a, npairs, k.sh, bytes);
+                case 3:  return launch_flow_iter_t<128, 2, 4, 4, 3>(c, a, npairs, k.sh, bytes);
+                default: return launch_flow_iter_t<128, 2, 4, 4, 0>(c, a, npairs, k.sh, bytes);
+            }
+        case 12828: return launch_flow_iter_t<128, 2, 4, 8>(c, a, npairs, k.sh, bytes);
+        case 12848: return launch_flow_iter_t<128, 4, 4, 8>(c, a, npairs, k.sh, bytes);
+        case 12844: return launch_flow_iter_t<128, 4, 4, 4>(c, a, npairs, k.sh, bytes);
+        case 16024: return launch_flow_iter_t<160, 2, 3, 4>(c, a, npairs, k.sh, bytes);
+        case 16028: return launch_flow_iter_t<160, 2, 3, 8>(c, a, npairs, k.sh, bytes);
+        case 25624: return launch_flow_iter_t<256, 2, 2, 4>(c, a, npairs, k.sh, bytes);
+        case 25628: return launch_flow_iter_t<256, 2, 2, 8>(c, a, npairs, k.sh, bytes);
+        case 25648: return launch_flow_iter_t<256, 4, 2, 8>(c, a, npairs, k.sh, bytes);
+        case 9624:  return launch_flow_iter_t<96, 2, 5, 4>(c, a, npairs, k.sh, bytes);
         default: break;
     }
-    // Frames under 1280x720 (the reference's 256x256 product mode, 640x360): 160-thread strips of up to 144 outputs, so a
-    // 256-column level is 2 strips instead of 3 and a 128-column level 1 instead of 2: +10 % at 256x256; at 1080p the
-    // same variant loses 3 % (3 CTAs / SM), so large frames keep 128 threads (profiles/r1_sweep_segments.txt).
-    {
-        const long long frame_px = c->seg_frame_px > 0 ? c->seg_frame_px : (long long)w * h;
-        if (key == 12826 && tx == 0 && frame_px < 1280LL * 720)
-            return launch_flow_iter_t<160, 2, 3, true>(c, a, npairs, k.sh, bytes);
-    }
-    // default: 128 threads x 2 rows per step, horizontal phase first; TX = loads moved to the texture pipe
-    switch (tx) {
-        case 1:  return launch_flow_iter_t<128, 2, 4, true, 4, false, 1>(c, a, npairs, k.sh, bytes);
-        case 2:  return launch_flow_iter_t<128, 2, 4, true, 4, false, 2>(c, a, npairs, k.sh, bytes);
-        case 3:  return launch_flow_iter_t<128, 2, 4, true, 4, false, 3>(c, a, npairs, k.sh, bytes);
-        case 4:  return launch_flow_iter_t<128, 2, 4, true, 4, false, 4>(c, a, npairs, k.sh, bytes);
-        default: return launch_flow_iter_t<128, 2, 4, true>(c, a, npairs, k.sh, bytes);
-    }
+    return fail(c, FFB_E_INVALID, "FFB_ITER_CFG: no k_flow_iter variant %dx%dx%d", nt, u, ho);
 }
 
 // ------------------------------------------------------------------ geometry
@@ -645,7 +571,6 @@ void free_geometry(ffb_ctx* c) {
         dev_free(L.I); dev_free(L.fA); dev_free(L.fB);
         L = Level();
     }
-    free_textures(c);
     dev_free(c->R); dev_free(c->ring);
     for (int b = 0; b < 2; ++b) {
         dev_free(c->d_u8[b]);
@@ -707,9 +632,8 @@ int configure(ffb_ctx* c, int W, int H, int B, int maxPairs) {
         TRY(dev_alloc(c, &L.fA, (size_t)B * L.fp * L.h));
         TRY(dev_alloc(c, &L.fB, (size_t)B * L.fp * L.h));
     }
-    c->r_slot_floats = (off + 127) / 128 * 128;      // 512-byte multiples: texture views of the elements need it
+    c->r_slot_floats = (off + 127) / 128 * 128;      // 512-byte multiples
     TRY(dev_alloc(c, &c->R, (size_t)c->S * c->r_slot_floats));
-    TRY(make_ring_textures(c));
     c->fp0 = c->lev[p.n - 1].fp;
     c->ring_stride = (size_t)c->fp0 * H;
     TRY(dev_alloc(c, &c->ring, (size_t)c->ring_n * c->ring_stride));
@@ -866,13 +790,12 @@ int flow_pairs(ffb_ctx* c, int p0, int np) {
                         up.src = C.fB + (size_t)off * up.stride; up.sp = C.fp; up.wc = C.w; up.hc = C.h;
                     }
                     rc = launch_flow_iter(c, R, L.plane, L.rp, L.w, L.h, fin0 ? fin0 + (size_t)off * fstride : nullptr, fstride,
-                                          L.fp, toB, L.fp, cnt, &up, (long long)L.r_off);
+                                          L.fp, toB, L.fp, cnt, &up);
                 } else if (it == 1) {
-                    rc = launch_flow_iter(c, R, L.plane, L.rp, L.w, L.h, L.fB + (size_t)off * fstride, fstride, L.fp, toA, L.fp, cnt,
-                                          nullptr, (long long)L.r_off);
+                    rc = launch_flow_iter(c, R, L.plane, L.rp, L.w, L.h, L.fB + (size_t)off * fstride, fstride, L.fp, toA, L.fp, cnt);
                 } else {
                     rc = launch_flow_iter(c, R, L.plane, L.rp, L.w, L.h, L.fA + (size_t)off * fstride, fstride, L.fp,
-                                          last ? toRing : toB, L.fp, cnt, nullptr, (long long)L.r_off);
+                                          last ? toRing : toB, L.fp, cnt);
                 }
                 c->launch_stream = c->s_comp;
                 TRY(rc);

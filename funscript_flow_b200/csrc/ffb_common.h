@@ -6,9 +6,6 @@
 #define FFB_LAUNCH(kernel, grid, block, smem, stream, ...) \
     emu::launch((grid), (block), (smem), [=]() { kernel(__VA_ARGS__); })
 #define FFB_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::g_dyn_smem)
-// launch with thread-block clusters of (cx, cy, cz) CTAs
-#define FFB_LAUNCH_CLUSTER(kernel, grid, block, smem, stream, cx, cy, cz, arg) \
-    emu::launch((grid), (block), (smem), [=]() { kernel(arg); }, dim3((cx), (cy), (cz)))
 #else
 #include <cuda_runtime.h>
 #define FFB_LAUNCH(kernel, grid, block, smem, stream, ...) \
@@ -16,45 +13,10 @@
 #define FFB_DYN_SMEM(type, name) \
     extern __shared__ __align__(16) unsigned char ffb_dyn_smem_raw[]; \
     type* name = reinterpret_cast<type*>(ffb_dyn_smem_raw)
-#define FFB_LAUNCH_CLUSTER(kernel, grid_, block_, smem_, strm_, cx, cy, cz, arg)        \
-    do {                                                                                 \
-        cudaLaunchConfig_t cfg_ = {};                                                    \
-        cfg_.gridDim = (grid_); cfg_.blockDim = (block_);                                \
-        cfg_.dynamicSmemBytes = (smem_); cfg_.stream = (strm_);                          \
-        cudaLaunchAttribute at_[1];                                                      \
-        at_[0].id = cudaLaunchAttributeClusterDimension;                                 \
-        at_[0].val.clusterDim.x = (cx); at_[0].val.clusterDim.y = (cy); at_[0].val.clusterDim.z = (cz); \
-        cfg_.attrs = at_; cfg_.numAttrs = 1;                                             \
-        cudaLaunchKernelEx(&cfg_, kernel, arg);                                          \
-    } while (0)
 #endif
 
 #include <stddef.h>
 #include <stdint.h>
-
-// ---- thread-block clusters / distributed shared memory (sm_90+; emulated in the CPU test build)
-#ifdef FFB_EMU
-static inline unsigned ffb_cluster_rank() { return emu::cluster_rank(); }
-static inline void ffb_cluster_sync() { emu::cluster_sync(); }
-static inline void ffb_dsmem_store(float* local_addr, unsigned rank, float v) { *emu::map_shared(local_addr, rank) = v; }
-#else
-__device__ __forceinline__ unsigned ffb_cluster_rank() {
-    unsigned r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-// all threads of all CTAs of the cluster; release/acquire makes the DSMEM stores visible
-__device__ __forceinline__ void ffb_cluster_sync() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// store `v` at the address that `local_addr` has in the shared memory of CTA `rank` of this cluster
-__device__ __forceinline__ void ffb_dsmem_store(float* local_addr, unsigned rank, float v) {
-    const unsigned laddr = (unsigned)__cvta_generic_to_shared(local_addr);
-    unsigned raddr;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(laddr), "r"(rank));
-    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(raddr), "f"(v) : "memory");
-}
-#endif
 
 // ---- 256-bit global store (sm_100+, STG.E.ENL2.256): eight floats at a 32-byte aligned address.
 // A thread that owns 32 contiguous bytes fills a whole DRAM/L2 sector with one instruction instead of

@@ -530,35 +530,55 @@ __global__ void __launch_bounds__(256) k_update_matrices(FfbMatArgs a) {
 // ======================================================================================
 // One CTA owns a strip of SW output columns (plus a 7-column halo on each side: one thread per
 // M column) and marches down a segment of SH rows, U rows per step.  The matrices never touch HBM:
-//   * each thread gathers the inputs of the 5-vector M of its column for U new rows.  All loads are
+//   * each thread gathers the inputs of the 5-vector M of its column, two rows at a time.  All loads are
 //     unconditional (the R1 footprint is clamped into the image and the out-of-bounds fallback is
-//     selected afterwards), so the 25*U loads of a step are issued back to back, and they are
-//     issued BEFORE the horizontal phase of the previous step so their latency overlaps it; the
-//     flow of the next step is prefetched one step ahead (it feeds the gather addresses),
+//     selected afterwards), so the 20 loads of a row pair are issued back to back; the flow of the next
+//     step is prefetched one step ahead (it feeds the gather addresses),
 //   * a Kahan-compensated running sum over the last 15 rows is kept per column (the column ring of
 //     raw M values lives in shared memory so the row leaving the window can be subtracted),
-//   * the vertical sums are published to a double-buffered shared row buffer,
-//   * a quarter of the threads form the horizontal 15-sums for 4 adjacent outputs from five aligned
-//     16-byte shared loads per channel, solve the 2x2 system and store float2 x 4.
+//   * the vertical sums are published to a shared row buffer,
+//   * the first U * (SW / HO) threads form the horizontal 15-sums for HO adjacent outputs from aligned
+//     16-byte shared loads, solve the 2x2 system and store the flow vectors.  The horizontal phase of
+//     step s-1 runs at the top of step s, before that step's loads are issued (fewer live registers).
+// Warps whose 32 columns lie entirely beyond the strip's last needed column (the last strip of a level,
+// narrow levels) skip the gather and the vertical sums; they only meet the barriers.
 struct FfbIterArgs {
     FfbRing R;              // frame expansions: pair j uses elements j (prev) and j+1 (next)
     int plane; int rp; int w, h;                     // plane = rp * h floats (< 2^31 / 5)
     const float2* fin; size_t fin_stride; int fip;   // flow in (NULL = zero), strides in float2
     FfbRing fout; int fop;                           // flow out ring (element j), pitch in float2
-    int SW;                 // output columns per strip (multiple of 4, <= NT - 14)
-    int SH;                 // rows per segment
+    int SW;                 // output columns per strip (multiple of HO, <= NT - 14)
+    int SH;                 // rows per segment (even)
     // A1e fused (exact 2:1 levels only): when up_src != NULL the incoming flow is the coarser level's
     // result, up-sampled and doubled on the fly instead of being read from `fin`.
     const float2* up_src; size_t up_stride; int usp; int wc, hc;
-    // TX > 0: part of the R1 footprint is fetched through the texture pipe.  One float4 view and one
-    // float view (linear-memory texture objects) per element of the expansion ring `R`; texA / texB are
-    // the texel offsets of this level's float4 image / xy plane inside a ring element.
-    const cudaTextureObject_t* tex4; const cudaTextureObject_t* tex1; unsigned texA, texB;
 };
 
-template <int NT, int U, bool CL = false>
+// OPT bits of k_flow_iter (measured variants):
+constexpr int FFB_IT_STREAM = 1;     // R0 and flow-in loads do not allocate in L1 (they are used once per CTA)
+constexpr int FFB_IT_PREFETCH = 2;   // one thread bulk-prefetches the rows of step s + 4 into L2
+
+// Shared row buffer of the vertical sums, one row of NT positions per (buffer, row of the step, channel).
+// HO = 4: position p is stored at p.  HO = 8: a task reads the six 16-byte vectors 2g .. 2g+5 (g = task
+// index), i.e. lanes are 32 bytes apart and a quarter-warp would hit every bank twice; the even and the
+// odd vectors are therefore stored in two separate halves, so that the k-th load of consecutive tasks
+// reads consecutive vectors (conflict-free), and the halves are 16 banks apart so that the 32 scalar
+// stores of a publishing warp (16 to each half) do not collide either.
+template <int NT, int HO>
+struct FfbHrowLayout {
+    static constexpr int HALF = NT / 2;
+    static constexpr int HOFF = HO == 8 ? (HALF % 32 == 16 ? HALF : (HALF + 31) / 32 * 32 + 16) : 0;
+    static constexpr int PITCH = HO == 8 ? HOFF + HALF : NT + 4;            // floats per (row, channel)
+    static constexpr int RSTRIDE = HO == 8 ? 5 * PITCH + ((24 - (5 * PITCH) % 32) + 32) % 32 : 5 * PITCH;   // per row of a step
+    __device__ __forceinline__ static int idx(int p) {
+        return HO == 8 ? ((p >> 2) & 1) * HOFF + ((p >> 3) << 2) + (p & 3) : p;
+    }
+};
+
+template <int NT, int U, int HO>
 __host__ __device__ constexpr size_t ffb_flow_iter_smem() {
-    return sizeof(float) * (2 * U * 5 * (CL ? NT + 16 : NT + 4) + FFB_WIN * 5 * NT);
+    // U = 2: the row buffer is double-buffered (one barrier per step); U = 4: single buffer, two barriers
+    return sizeof(float) * ((U == 2 ? 2 : 1) * U * FfbHrowLayout<NT, HO>::RSTRIDE + FFB_WIN * 5 * NT);
 }
 
 // Raw inputs of one matrix update, as loaded (all loads unconditional).
@@ -570,17 +590,40 @@ struct FfbGather {
     int inside;
 };
 
+// global loads that do not allocate in L1 (streams that a CTA reads once)
+#ifdef FFB_EMU
+static inline float4 ffb_ldg_stream4(const float4* p) { return *p; }
+static inline float2 ffb_ldg_stream2(const float2* p) { return *p; }
+static inline float ffb_ldg_stream1(const float* p) { return *p; }
+static inline void ffb_prefetch_l2(const void*, unsigned) {}
+#else
+__device__ __forceinline__ float4 ffb_ldg_stream4(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float2 ffb_ldg_stream2(const float2* p) {
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ffb_ldg_stream1(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+// bulk prefetch of `bytes` (multiple of 16) at a 16-byte aligned address into L2
+__device__ __forceinline__ void ffb_prefetch_l2(const void* p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+#endif
+
 // Expansion layout (written by k_polyexp): per frame-level a float4 image A[h][rp] holding
 // (d/dy, d/dx, yy, xx) per pixel followed by a float plane B[h][rp] holding xy.  A 2x2 bilinear
 // footprint is then 4 x 16-byte + 4 x 4-byte loads off two row addresses instead of 20 scalar loads.
-// TX selects which loads of the R1 footprint go through the texture pipe instead of the LSU pipe (the
-// kernel is bound by LSU data-pipe wavefronts, shared + global; the texture pipe is otherwise idle):
-// 0 none, 1 the four xy scalars, 2 + the (y1+1, x1+1) vector, 4 + the whole y1+1 row, 3 everything.
-// Same addresses, same values: the result does not depend on TX.
-template <int TX>
+template <bool STREAM>
 __device__ __forceinline__ void ffb_gather_issue(const float4* __restrict__ A0, const float* __restrict__ B0,
                                                  const float4* __restrict__ A1, const float* __restrict__ B1,
-                                                 cudaTextureObject_t T4, cudaTextureObject_t T1, unsigned texA, unsigned texB,
                                                  int rp, int w, int h, int x, int y, float2 d, FfbGather& g) {
     float fx = (float)x + d.x, fy = (float)y + d.y;
     const float x1f = floorf(fx), y1f = floorf(fy);
@@ -592,29 +635,21 @@ __device__ __forceinline__ void ffb_gather_issue(const float4* __restrict__ A0, 
     g.inside = ((unsigned)x1 < (unsigned)(w - 1)) && ((unsigned)y1 < (unsigned)(h - 1));
     const int xs = min(max(x1, 0), w - 2), ys = min(max(y1, 0), h - 2);
     const unsigned o0 = (unsigned)(y * rp + x), o1 = (unsigned)(ys * rp + xs);
-    const float4 q = __ldg(A0 + o0);
-    const float q4 = __ldg(B0 + o0);
-    const int ia = (int)(texA + o1), ib = (int)(texB + o1);
-    const float4 t00 = TX == 3 ? tex1Dfetch<float4>(T4, ia) : __ldg(A1 + o1);
-    const float4 t01 = TX == 3 ? tex1Dfetch<float4>(T4, ia + 1) : __ldg(A1 + o1 + 1);
-    const float4 t10 = TX >= 3 ? tex1Dfetch<float4>(T4, ia + rp) : __ldg(A1 + o1 + rp);
-    const float4 t11 = TX >= 2 ? tex1Dfetch<float4>(T4, ia + rp + 1) : __ldg(A1 + o1 + rp + 1);
+    const float4 q = STREAM ? ffb_ldg_stream4(A0 + o0) : __ldg(A0 + o0);
+    const float q4 = STREAM ? ffb_ldg_stream1(B0 + o0) : __ldg(B0 + o0);
+    const float4 t00 = __ldg(A1 + o1);
+    const float4 t01 = __ldg(A1 + o1 + 1);
+    const float4 t10 = __ldg(A1 + o1 + rp);
+    const float4 t11 = __ldg(A1 + o1 + rp + 1);
     g.r0[0] = q.x; g.r0[1] = q.y; g.r0[2] = q.z; g.r0[3] = q.w; g.r0[4] = q4;
     g.t[0][0] = t00.x; g.t[0][1] = t01.x; g.t[0][2] = t10.x; g.t[0][3] = t11.x;
     g.t[1][0] = t00.y; g.t[1][1] = t01.y; g.t[1][2] = t10.y; g.t[1][3] = t11.y;
     g.t[2][0] = t00.z; g.t[2][1] = t01.z; g.t[2][2] = t10.z; g.t[2][3] = t11.z;
     g.t[3][0] = t00.w; g.t[3][1] = t01.w; g.t[3][2] = t10.w; g.t[3][3] = t11.w;
-    if (TX >= 1) {
-        g.t[4][0] = tex1Dfetch<float>(T1, ib);
-        g.t[4][1] = tex1Dfetch<float>(T1, ib + 1);
-        g.t[4][2] = tex1Dfetch<float>(T1, ib + rp);
-        g.t[4][3] = tex1Dfetch<float>(T1, ib + rp + 1);
-    } else {
-        g.t[4][0] = __ldg(B1 + o1);
-        g.t[4][1] = __ldg(B1 + o1 + 1);
-        g.t[4][2] = __ldg(B1 + o1 + rp);
-        g.t[4][3] = __ldg(B1 + o1 + rp + 1);
-    }
+    g.t[4][0] = __ldg(B1 + o1);
+    g.t[4][1] = __ldg(B1 + o1 + 1);
+    g.t[4][2] = __ldg(B1 + o1 + rp);
+    g.t[4][3] = __ldg(B1 + o1 + rp + 1);
 }
 
 __device__ __forceinline__ void ffb_gather_finish(const FfbGather& g, int w, int h, int x, int y, float m[5]) {
@@ -660,88 +695,72 @@ __device__ __forceinline__ void ffb_up2(int d, int src_n, int& i0, int& i1, floa
     i1 = min(i0 + 1, src_n - 1);
 }
 
-// CL: the strips of two CTAs form a thread-block cluster that covers 2*NT contiguous matrix columns;
-// each CTA computes the vertical sums of its own NT columns only and the few columns next to the seam
-// are exchanged through distributed shared memory (each boundary thread also stores its sums into
-// the partner's row buffer), so the 14-column halo is paid once per cluster instead of once per CTA.
-template <int NT, int U, int MINB, bool HFIRST, bool UP2X, int HO, bool CL, int TX = 0>
+// box mean -> 2x2 solve of one output (sums of the 15x15 window of the five matrix channels)
+__device__ __forceinline__ float2 ffb_solve(float s0, float s1, float s2, float s3, float s4) {
+    const float sc = 1.f / (float)(FFB_WIN * FFB_WIN);
+    const float g11 = s0 * sc, g12 = s1 * sc, g22 = s2 * sc, h1 = s3 * sc, h2 = s4 * sc;
+    // det = g11*g22 - g12*g12 with an exact-product correction (Kahan's ad-bc)
+    const float wq = g12 * g12;
+    const float e = __fmaf_rn(-g12, g12, wq);
+    const float fd = __fmaf_rn(g11, g22, -wq);
+    const float den = (fd + e) + 1e-3f;
+    float idet = __fdividef(1.f, den);              // approximate reciprocal ...
+    idet = idet * __fmaf_rn(-den, idet, 2.f);       // ... plus one Newton step (<= 1 ulp, no slow path)
+    float2 o;
+    o.x = (g11 * h2 - g12 * h1) * idet;
+    o.y = (g22 * h1 - g12 * h2) * idet;
+    return o;
+}
+
+template <int NT, int U, int MINB, bool UP2X, int HO, int OPT>
 __global__ void __launch_bounds__(NT, MINB) k_flow_iter(FfbIterArgs a) {
     static_assert(HO == 4 || HO == 8, "outputs per horizontal task");
-    constexpr int HP = CL ? NT + 16 : NT + 4;
-    // dynamic shared memory (exceeds the 48 KB static limit): hrow first (16-byte aligned), then ring
+    static_assert(U == 2 || U == 4, "rows per step");
+    using HL = FfbHrowLayout<NT, HO>;
+    constexpr int NB = U == 2 ? 2 : 1;               // row buffers
+    constexpr bool STREAM = (OPT & FFB_IT_STREAM) != 0;
+    // dynamic shared memory (exceeds the 48 KB static limit): row buffer first (16-byte aligned), then the ring
     FFB_DYN_SMEM(float, smem_f);
-    typedef float (*HrowT)[U][5][HP];
+    float* hrow = smem_f;                                               // [NB][U] rows of RSTRIDE floats: [5][PITCH]
     typedef float (*RingT)[5][NT];
-    HrowT hrow = reinterpret_cast<HrowT>(smem_f);                       // [2][U][5][HP]
-    RingT ring = reinterpret_cast<RingT>(smem_f + 2 * U * 5 * HP);      // [FFB_WIN][5][NT]
+    RingT ring = reinterpret_cast<RingT>(smem_f + NB * U * HL::RSTRIDE);   // [FFB_WIN][5][NT]
     const int tid = threadIdx.x;
     const int pair = blockIdx.x;      // fastest-varying: see the launcher
     const float4* A0 = reinterpret_cast<const float4*>(ffb_ring_at(a.R, pair));
     const float4* A1 = reinterpret_cast<const float4*>(ffb_ring_at(a.R, pair + 1));
     const float* B0 = reinterpret_cast<const float*>(A0 + a.plane);
     const float* B1 = reinterpret_cast<const float*>(A1 + a.plane);
-    const int slot1 = (a.R.first + pair + 1) % a.R.mod;
-    const cudaTextureObject_t T4 = TX >= 2 ? a.tex4[slot1] : 0, T1 = TX >= 1 ? a.tex1[slot1] : 0;
     const float2* fin = a.fin ? a.fin + (size_t)pair * a.fin_stride : nullptr;
     float2* fout = reinterpret_cast<float2*>(ffb_ring_at(a.fout, pair));
     const int w = a.w, h = a.h;
-    // CL: a.SW = outputs per CTA; cluster c covers outputs [2c*SW, 2c*SW + 2*SW) and matrix columns
-    // xoc - 7 .. xoc + 2*NT - 8, CTA `crank` owning columns crank*NT .. crank*NT + NT - 1 of them
-    const unsigned crank = CL ? ffb_cluster_rank() : 0u;
-    const int xoc = CL ? (int)(blockIdx.y >> 1) * 2 * a.SW : 0;
-    const int xo0 = CL ? xoc + (int)crank * a.SW : (int)blockIdx.y * a.SW;
-    const int xc = ffb_clampi((CL ? xoc + (int)crank * NT : xo0) - FFB_WIN_R + tid, 0, w - 1);
-    // position of this thread's column in the CTA's row buffer; window of output j starts at position j
-    const int own_off = (CL && crank == 1) ? NT - a.SW : 0;
-    // seam columns: CTA 0's columns >= SW are positions tid - SW of CTA 1; CTA 1's columns < SW + 14 - NT
-    // are positions NT + tid of CTA 0
-    const bool seam = CL && (crank == 0 ? tid >= a.SW : tid < a.SW + 2 * FFB_WIN_R - NT);
-    const int seam_pos = crank == 0 ? tid - a.SW : NT + tid;
+    const int xo0 = (int)blockIdx.y * a.SW;
+    const int useful = min(a.SW, w - xo0);                  // outputs of this strip
+    const int xc = ffb_clampi(xo0 - FFB_WIN_R + tid, 0, w - 1);
+    // a warp is live when at least one of its columns is a matrix column the strip's outputs need
+    const bool live = (tid & ~31) < useful + 2 * FFB_WIN_R;
+    const int hpos = HL::idx(tid);
     const int y0 = blockIdx.z * a.SH;
     const int y1 = min(y0 + a.SH, h);
     const int nfeed = (y1 - y0) + 2 * FFB_WIN_R;
     const int nsteps = (nfeed + U - 1) / U;
-    const int groups = a.SW / HO;
     // horizontal-phase role of this thread (fixed for the whole kernel)
+    const int groups = (useful + HO - 1) / HO;
     const bool hz = tid < U * groups;
     const int hu = hz ? tid / groups : 0;
     const int hg = hz ? tid - hu * groups : 0;
     const int hx = xo0 + HO * hg;
 
+    if (live) {
 #pragma unroll
-    for (int s = 0; s < FFB_WIN; ++s)
+        for (int s = 0; s < FFB_WIN; ++s)
 #pragma unroll
-        for (int c = 0; c < 5; ++c) ring[s][c][tid] = 0.f;
-    if (!CL && tid < 4) {
-#pragma unroll
-        for (int b = 0; b < 2; ++b)
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-#pragma unroll
-                for (int c = 0; c < 5; ++c) hrow[b][u][c][NT + tid] = 0.f;
+            for (int c = 0; c < 5; ++c) ring[s][c][tid] = 0.f;
     }
-    if (CL) {   // positions never written by either CTA are read (not used) by the last 16-byte loads
-        if (tid < 16) {
-            const int pos = crank == 0 ? NT + tid : tid;      // CTA 0: tail beyond its columns; CTA 1: head before own_off
+    if (HO == 4 && tid < 4) {      // positions NT .. NT+3 are read (not used) by the last task's 16-byte loads
 #pragma unroll
-            for (int b = 0; b < 2; ++b)
+        for (int b = 0; b < NB * U; ++b)
 #pragma unroll
-                for (int u = 0; u < U; ++u)
-#pragma unroll
-                    for (int c = 0; c < 5; ++c) hrow[b][u][c][pos] = 0.f;
-        }
-        if (crank == 1 && tid < 16) {
-            const int pos = own_off + NT + tid;
-            if (pos < HP) {
-#pragma unroll
-                for (int b = 0; b < 2; ++b)
-#pragma unroll
-                    for (int u = 0; u < U; ++u)
-#pragma unroll
-                        for (int c = 0; c < 5; ++c) hrow[b][u][c][pos] = 0.f;
-            }
-        }
-        ffb_cluster_sync();      // the partner must not store into this buffer before it is initialised
+            for (int c = 0; c < 5; ++c) hrow[b * HL::RSTRIDE + c * HL::PITCH + NT + tid] = 0.f;
     }
     float vs[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, comp[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     int slot = 0;
@@ -749,16 +768,19 @@ __global__ void __launch_bounds__(NT, MINB) k_flow_iter(FfbIterArgs a) {
     // horizontal sums + solve + store of the U rows published by step `s` into buffer `buf`
     auto horizontal = [&](int s, int buf) {
         const int i = s * U + hu;
-        if (!hz || i < 2 * FFB_WIN_R || i >= nfeed || hx >= w) return;
+        if (!hz || i < 2 * FFB_WIN_R || i >= nfeed) return;
         const int yo = y0 + i - 2 * FFB_WIN_R;
+        const float* hb = hrow + (buf * U + hu) * HL::RSTRIDE;
         if (HO == 8) {
-            // 8 adjacent outputs per task: 22 window elements from six 16-byte shared loads per channel;
+            // 8 adjacent outputs per task: 22 window elements from six 16-byte shared loads per channel
+            // (three from the even half, three from the odd half);
             // sum_j = (e7..e14) + (e_j..e6) + (e15..e_{14+j})
             float sum8[5][8];
 #pragma unroll
             for (int c = 0; c < 5; ++c) {
-                const float4* hp = reinterpret_cast<const float4*>(&hrow[buf][hu][c][8 * hg]);
-                const float4 q0 = hp[0], q1 = hp[1], q2 = hp[2], q3 = hp[3], q4 = hp[4], q5 = hp[5];
+                const float4* he = reinterpret_cast<const float4*>(hb + c * HL::PITCH + 4 * hg);
+                const float4* ho = reinterpret_cast<const float4*>(hb + c * HL::PITCH + HL::HOFF + 4 * hg);
+                const float4 q0 = he[0], q1 = ho[0], q2 = he[1], q3 = ho[1], q4 = he[2], q5 = ho[2];
                 const float e[24] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w,
                                      q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, q4.z, q4.w, q5.x, q5.y, q5.z, q5.w};
                 const float common = ((e[7] + e[8]) + (e[9] + e[10])) + ((e[11] + e[12]) + (e[13] + e[14]));
@@ -778,35 +800,23 @@ __global__ void __launch_bounds__(NT, MINB) k_flow_iter(FfbIterArgs a) {
             }
             float2 o8[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float sc = 1.f / (float)(FFB_WIN * FFB_WIN);
-                const float g11 = sum8[0][j] * sc, g12 = sum8[1][j] * sc, g22 = sum8[2][j] * sc;
-                const float h1 = sum8[3][j] * sc, h2 = sum8[4][j] * sc;
-                const float wq = g12 * g12;
-                const float e2 = __fmaf_rn(-g12, g12, wq);
-                const float fd = __fmaf_rn(g11, g22, -wq);
-                const float den = (fd + e2) + 1e-3f;
-                float idet = __fdividef(1.f, den);
-                idet = idet * __fmaf_rn(-den, idet, 2.f);
-                o8[j].x = (g11 * h2 - g12 * h1) * idet;
-                o8[j].y = (g22 * h1 - g12 * h2) * idet;
-            }
+            for (int j = 0; j < 8; ++j) o8[j] = ffb_solve(sum8[0][j], sum8[1][j], sum8[2][j], sum8[3][j], sum8[4][j]);
             float2* dst8 = fout + (yo * a.fop + hx);
-            if (hx + 7 < w) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    reinterpret_cast<float4*>(dst8)[j] = make_float4(o8[2 * j].x, o8[2 * j].y, o8[2 * j + 1].x, o8[2 * j + 1].y);
+            if (hx + 7 < w) {   // hx % 8 == 0, flow rows and buffers are 32-byte aligned (checked by the launcher)
+                ffb_store_f8(reinterpret_cast<float*>(dst8), make_float4(o8[0].x, o8[0].y, o8[1].x, o8[1].y),
+                             make_float4(o8[2].x, o8[2].y, o8[3].x, o8[3].y));
+                ffb_store_f8(reinterpret_cast<float*>(dst8 + 4), make_float4(o8[4].x, o8[4].y, o8[5].x, o8[5].y),
+                             make_float4(o8[6].x, o8[6].y, o8[7].x, o8[7].y));
             } else {
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     if (hx + j < w) dst8[j] = o8[j];
             }
-            return;
-        }
+        } else {
         float sum[5][4];
 #pragma unroll
         for (int c = 0; c < 5; ++c) {
-            const float4* hp = reinterpret_cast<const float4*>(&hrow[buf][hu][c][4 * hg]);
+            const float4* hp = reinterpret_cast<const float4*>(hb + c * HL::PITCH + 4 * hg);
             const float4 q0 = hp[0], q1 = hp[1], q2 = hp[2], q3 = hp[3], q4 = hp[4];
             // window of output 0 = elements 0..14; each next output drops one, adds one
             const float mid = ((q0.w + q1.x) + (q1.y + q1.z)) + ((q1.w + q2.x) + (q2.y + q2.z)) +
@@ -818,20 +828,7 @@ __global__ void __launch_bounds__(NT, MINB) k_flow_iter(FfbIterArgs a) {
         }
         float2 o[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float sc = 1.f / (float)(FFB_WIN * FFB_WIN);
-            const float g11 = sum[0][j] * sc, g12 = sum[1][j] * sc, g22 = sum[2][j] * sc;
-            const float h1 = sum[3][j] * sc, h2 = sum[4][j] * sc;
-            // det = g11*g22 - g12*g12 with an exact-product correction (Kahan's ad-bc)
-            const float wq = g12 * g12;
-            const float e = __fmaf_rn(-g12, g12, wq);
-            const float fd = __fmaf_rn(g11, g22, -wq);
-            const float den = (fd + e) + 1e-3f;
-            float idet = __fdividef(1.f, den);              // approximate reciprocal ...
-            idet = idet * __fmaf_rn(-den, idet, 2.f);       // ... plus one Newton step (<= 1 ulp, no slow path)
-            o[j].x = (g11 * h2 - g12 * h1) * idet;
-            o[j].y = (g22 * h1 - g12 * h2) * idet;
-        }
+        for (int j = 0; j < 4; ++j) o[j] = ffb_solve(sum[0][j], sum[1][j], sum[2][j], sum[3][j], sum[4][j]);
         float2* dst = fout + (yo * a.fop + hx);
         if (hx + 3 < w) {   // hx % 4 == 0, flow rows and buffers are 32-byte aligned (checked by the launcher)
             ffb_store_f8(reinterpret_cast<float*>(dst), make_float4(o[0].x, o[0].y, o[1].x, o[1].y),
@@ -840,6 +837,7 @@ __global__ void __launch_bounds__(NT, MINB) k_flow_iter(FfbIterArgs a) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 if (hx + j < w) dst[j] = o[j];
+        }
         }
     };
 
@@ -851,12 +849,13 @@ __global__ void __launch_bounds__(NT, MINB) k_flow_iter(FfbIterArgs a) {
     int ux0 = 0, ux1 = 0;
     float ual = 0.f;
     if (UP2X) ffb_up2(xc, a.wc, ux0, ux1, ual);
-    auto load_flow = [&](int s, float2 (&d)[U]) {
-        if (UP2X && U == 2) {
-            // The launcher makes SH even, so the two rows of a step are an (odd, even) pair of image rows (or
-            // both clamped to the same border row): they interpolate between the SAME two coarse rows, with
-            // weights 0.25 / 0.75.  Fetch and x-interpolate those rows once for both.
-            const int ya = ffb_clampi(y0 - FFB_WIN_R + s * 2, 0, h - 1), yb = ffb_clampi(y0 - FFB_WIN_R + s * 2 + 1, 0, h - 1);
+    // flow vectors of feed rows i0, i0 + 1 of the segment (i0 even) at this thread's column
+    auto load_flow2 = [&](int i0, float2& da, float2& db) {
+        const int ya = ffb_clampi(y0 - FFB_WIN_R + i0, 0, h - 1), yb = ffb_clampi(y0 - FFB_WIN_R + i0 + 1, 0, h - 1);
+        if (UP2X) {
+            // The launcher makes SH even, so the two rows are an (odd, even) pair of image rows (or both clamped
+            // to the same border row): they interpolate between the SAME two coarse rows, with weights
+            // 0.25 / 0.75.  Fetch and x-interpolate those rows once for both (same arithmetic as k_upsample_flow).
             int uy0, uy1, vy0, vy1;
             float be0, be1;
             ffb_up2(ya, a.hc, uy0, uy1, be0);
@@ -865,88 +864,110 @@ __global__ void __launch_bounds__(NT, MINB) k_flow_iter(FfbIterArgs a) {
             const float2 p10 = __ldg(ups + (uy1 * a.usp + ux0)), p11 = __ldg(ups + (uy1 * a.usp + ux1));
             const float tx = p00.x * (1.f - ual) + p01.x * ual, ty = p00.y * (1.f - ual) + p01.y * ual;
             const float bx = p10.x * (1.f - ual) + p11.x * ual, by = p10.y * (1.f - ual) + p11.y * ual;
-            d[0].x = (tx * (1.f - be0) + bx * be0) * 2.f;
-            d[0].y = (ty * (1.f - be0) + by * be0) * 2.f;
+            da.x = (tx * (1.f - be0) + bx * be0) * 2.f;
+            da.y = (ty * (1.f - be0) + by * be0) * 2.f;
             if (vy0 == uy0 && vy1 == uy1) {
-                d[1].x = (tx * (1.f - be1) + bx * be1) * 2.f;
-                d[1].y = (ty * (1.f - be1) + by * be1) * 2.f;
+                db.x = (tx * (1.f - be1) + bx * be1) * 2.f;
+                db.y = (ty * (1.f - be1) + by * be1) * 2.f;
             } else {   // not reached with an even SH; kept so that any segmentation stays correct
                 const float2 q00 = __ldg(ups + (vy0 * a.usp + ux0)), q01 = __ldg(ups + (vy0 * a.usp + ux1));
                 const float2 q10 = __ldg(ups + (vy1 * a.usp + ux0)), q11 = __ldg(ups + (vy1 * a.usp + ux1));
                 const float sx = q00.x * (1.f - ual) + q01.x * ual, sy = q00.y * (1.f - ual) + q01.y * ual;
                 const float cx = q10.x * (1.f - ual) + q11.x * ual, cy = q10.y * (1.f - ual) + q11.y * ual;
-                d[1].x = (sx * (1.f - be1) + cx * be1) * 2.f;
-                d[1].y = (sy * (1.f - be1) + cy * be1) * 2.f;
+                db.x = (sx * (1.f - be1) + cx * be1) * 2.f;
+                db.y = (sy * (1.f - be1) + cy * be1) * 2.f;
             }
-            return;
+        } else if (fin) {
+            da = STREAM ? ffb_ldg_stream2(fin + (ya * a.fip + xc)) : __ldg(fin + (ya * a.fip + xc));
+            db = STREAM ? ffb_ldg_stream2(fin + (yb * a.fip + xc)) : __ldg(fin + (yb * a.fip + xc));
+        } else {
+            da = db = make_float2(0.f, 0.f);
         }
+    };
+
+    // OPT & FFB_IT_PREFETCH: the first lane of the last warp asks L2 for the rows of step s + 4 (the expansion
+    // rows of both frames over the strip's columns, assuming the flow moves the footprint by less than 8
+    // pixels); requests that fall outside the image are clipped, not issued
+    auto prefetch_rows = [&](int s) {
+        if (!(OPT & FFB_IT_PREFETCH) || tid != NT - 32) return;
+        const int xa = max(xo0 - 2 * FFB_WIN_R - 1, 0) & ~3, xb = min(xo0 + a.SW + 2 * FFB_WIN_R + 1, w);
+        if (xb <= xa) return;
+        const unsigned n4 = (unsigned)(((xb - xa) + 3) & ~3);
+        const int ya = y0 - FFB_WIN_R + (s + 4) * U;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int yc = ffb_clampi(y0 - FFB_WIN_R + s * U + u, 0, h - 1);
-            if (UP2X) {   // same arithmetic as k_upsample_flow
-                int uy0, uy1;
-                float be;
-                ffb_up2(yc, a.hc, uy0, uy1, be);
-                const float2 p00 = __ldg(ups + (uy0 * a.usp + ux0)), p01 = __ldg(ups + (uy0 * a.usp + ux1));
-                const float2 p10 = __ldg(ups + (uy1 * a.usp + ux0)), p11 = __ldg(ups + (uy1 * a.usp + ux1));
-                const float tx = p00.x * (1.f - ual) + p01.x * ual, ty = p00.y * (1.f - ual) + p01.y * ual;
-                const float bx = p10.x * (1.f - ual) + p11.x * ual, by = p10.y * (1.f - ual) + p11.y * ual;
-                d[u].x = (tx * (1.f - be) + bx * be) * 2.f;
-                d[u].y = (ty * (1.f - be) + by * be) * 2.f;
-            } else {
-                d[u] = fin ? __ldg(fin + (yc * a.fip + xc)) : make_float2(0.f, 0.f);
+        for (int r = -1; r <= U; ++r) {
+            const int y = ya + r;
+            if (y < 0 || y >= h) continue;
+            const unsigned o = (unsigned)(y * a.rp + xa);
+            ffb_prefetch_l2(A1 + o, n4 * 16u);
+            ffb_prefetch_l2(B1 + o, n4 * 4u);
+            if (r >= 0 && r < U) {
+                ffb_prefetch_l2(A0 + o, n4 * 16u);
+                ffb_prefetch_l2(B0 + o, n4 * 4u);
             }
         }
     };
 
     float2 d[U], dn[U];
-    load_flow(0, d);
+    if (live) {
+#pragma unroll
+        for (int u = 0; u < U; u += 2) load_flow2(u, d[u], d[u + 1]);
+    }
     for (int s = 0; s < nsteps; ++s) {
-        const int buf = s & 1;
-        // HFIRST: run the horizontal phase of the previous step before issuing this step's loads
-        // (lower register pressure, relies on the other resident warps to cover the load latency)
-        if (HFIRST && s > 0) horizontal(s - 1, buf ^ 1);
-        // ---- issue the gather of step s (10*U independent loads), then the flow prefetch of step s+1
-        FfbGather g[U];
+        const int buf = NB == 2 ? (s & 1) : 0;
+        // the horizontal phase of the previous step runs before this step's loads are issued
+        // (lower register pressure; the other resident warps cover the load latency)
+        if (s > 0) horizontal(s - 1, NB == 2 ? (buf ^ 1) : 0);
+        prefetch_rows(s);
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int yc = ffb_clampi(y0 - FFB_WIN_R + s * U + u, 0, h - 1);
-            ffb_gather_issue<TX>(A0, B0, A1, B1, T4, T1, a.texA, a.texB, a.rp, w, h, xc, yc, d[u], g[u]);
-        }
-        load_flow(s + 1, dn);
-        // ---- while those are in flight: horizontal phase of the previous step
-        if (!HFIRST && s > 0) horizontal(s - 1, buf ^ 1);
-        // ---- matrices + vertical running sums (Kahan-compensated add of  new - leaving)
+        for (int hh = 0; hh < U; hh += 2) {
+            float vrow[2][5];
+            if (live) {
+                // ---- issue the gather of rows hh, hh + 1 (20 independent loads), then the flow prefetch of step s+1
+                FfbGather g[2];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int i = s * U + u;
-            if (i < nfeed) {
-                const int yc = ffb_clampi(y0 - FFB_WIN_R + i, 0, h - 1);
-                float m[5];
-                ffb_gather_finish(g[u], w, h, xc, yc, m);
-#pragma unroll
-                for (int c = 0; c < 5; ++c) {
-                    const float old = ring[slot][c][tid];
-                    ring[slot][c][tid] = m[c];
-                    const float yk = (m[c] - old) - comp[c];
-                    const float t = vs[c] + yk;
-                    comp[c] = (t - vs[c]) - yk;
-                    vs[c] = t;
+                for (int u = 0; u < 2; ++u) {
+                    const int yc = ffb_clampi(y0 - FFB_WIN_R + s * U + hh + u, 0, h - 1);
+                    ffb_gather_issue<STREAM>(A0, B0, A1, B1, a.rp, w, h, xc, yc, d[hh + u], g[u]);
                 }
-                slot = slot + 1 == FFB_WIN ? 0 : slot + 1;
+                load_flow2((s + 1) * U + hh, dn[hh], dn[hh + 1]);
+                // ---- matrices + vertical running sums (Kahan-compensated add of  new - leaving)
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int i = s * U + hh + u;
+                    if (i < nfeed) {
+                        const int yc = ffb_clampi(y0 - FFB_WIN_R + i, 0, h - 1);
+                        float m[5];
+                        ffb_gather_finish(g[u], w, h, xc, yc, m);
+#pragma unroll
+                        for (int c = 0; c < 5; ++c) {
+                            const float old = ring[slot][c][tid];
+                            ring[slot][c][tid] = m[c];
+                            const float yk = (m[c] - old) - comp[c];
+                            const float t = vs[c] + yk;
+                            comp[c] = (t - vs[c]) - yk;
+                            vs[c] = t;
+                        }
+                        slot = slot + 1 == FFB_WIN ? 0 : slot + 1;
+                    }
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) vrow[u][c] = vs[c];
+                }
             }
+            // single row buffer: the horizontal phase of step s-1 must have read it before it is overwritten
+            if (NB == 1 && hh == 0) __syncthreads();
+            if (live) {
 #pragma unroll
-            for (int c = 0; c < 5; ++c) hrow[buf][u][c][own_off + tid] = vs[c];
-            if (seam) {
+                for (int u = 0; u < 2; ++u)
 #pragma unroll
-                for (int c = 0; c < 5; ++c) ffb_dsmem_store(&hrow[buf][u][c][seam_pos], crank ^ 1u, vs[c]);
+                    for (int c = 0; c < 5; ++c) hrow[(buf * U + hh + u) * HL::RSTRIDE + c * HL::PITCH + hpos] = vrow[u][c];
             }
         }
-        if (CL) ffb_cluster_sync(); else __syncthreads();
+        __syncthreads();
 #pragma unroll
         for (int u = 0; u < U; ++u) d[u] = dn[u];
     }
-    horizontal(nsteps - 1, (nsteps - 1) & 1);
+    horizontal(nsteps - 1, NB == 2 ? ((nsteps - 1) & 1) : 0);
 }
 
 // ======================================================================================

@@ -157,29 +157,9 @@ def test_headless_folder_sharded_over_ranks(emu_ctx, tmp_path, monkeypatch):
     assert {k: json.load(open(str(tmp_path / f"v{k}.funscript"))) for k in range(3)} == single
 
 
-def test_cluster_variant_in_subprocess(emu_lib):
-    """The opt-in thread-block-cluster variant of k_flow_iter (two CTAs share the strip seam through
-    distributed shared memory; FFB_ITER_CFG=128x2x8 -- measured slower on B200, kept as an experiment):
-    the emulator runs both CTAs of a cluster as interleaved fibers with a cluster barrier and DSMEM."""
-    import os
-    import subprocess
-    import sys
-    code = (
-        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
-        "from funscript_flow_b200 import _native\n"
-        "import parity_checks as pc\n"
-        "ctx = _native.FlowContext(0, %r)\n"
-        "print(pc.check_farneback_vs_cv2(ctx, 480, 136))\n"
-        "pc.check_batch_independence(ctx, 480, 72, n_frames=6)\n"
-    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)), emu_lib)
-    env = dict(os.environ, FFB_ITER_CFG="128x2x8")
-    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
-    assert res.returncode == 0, res.stdout + res.stderr
-
-
 def test_large_frame_variant_in_subprocess(emu_lib, golden_dir):
     """Frames under 1280x720 run the 160-thread strips, so the small frames of this CPU suite would never reach the
-    128-thread kernel that 1080p and 4K use: FFB_ITER_CFG=128x2x5 forces it (the GPU suite covers it at full size)."""
+    128-thread kernel that 1080p and 4K use: FFB_ITER_CFG=128x2x4 forces it (the GPU suite covers it at full size)."""
     import os
     import subprocess
     import sys
@@ -192,15 +172,17 @@ def test_large_frame_variant_in_subprocess(emu_lib, golden_dir):
         "pc.check_batch_independence(ctx, 300, 72, n_frames=6)\n"
         "pc.check_golden_bracket(ctx, %r)\n"
     ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)), emu_lib, golden_dir)
-    env = dict(os.environ, FFB_ITER_CFG="128x2x5")
+    env = dict(os.environ, FFB_ITER_CFG="128x2x4")
     res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout + res.stderr
 
 
-@pytest.mark.parametrize("cfg", ["160x2x6", "96x2x6"])
-def test_wide_strip_variant_in_subprocess(emu_lib, cfg):
-    """Strip widths forced on any frame size: FFB_ITER_CFG=160x2x6 (144 output columns per CTA; the default for frames
-    under 1280x720) and 96x2x6 (80 columns; prepared for the levels under 128 columns, not measured yet)."""
+@pytest.mark.parametrize("cfg", ["160x2x4", "96x2x4", "128x4x8", "256x2x8"])
+def test_strip_variants_in_subprocess(emu_lib, cfg):
+    """k_flow_iter variants forced on any frame size with FFB_ITER_CFG=NTxUxHO (threads per strip x rows per step x
+    outputs per horizontal task): 160x2x4 is the default for frames under 1280x720; 128x4x8 exercises the single
+    row buffer with two barriers per step and the de-interleaved row layout of the 8-output tasks; 256x2x8 the widest
+    strips; 96x2x4 narrow ones.  Frames narrower than a strip also exercise the idle-warp path."""
     import os
     import subprocess
     import sys
