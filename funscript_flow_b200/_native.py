@@ -50,7 +50,12 @@ def load(path: Optional[str] = None) -> C.CDLL:
         "ffb_host_alloc": (i32, [C.POINTER(vp), sz]),
         "ffb_host_free": (i32, [vp]),
         "ffb_configure": (i32, [vp, i32, i32, i32, i32]),
+        "ffb_get_geometry": (i32, [vp, i32p, i32p, i32p, i32p]),
+        "ffb_alloc_counts": (i32, [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
         "ffb_bracket_begin": (i32, [vp, i32, C.c_double]),
+        "ffb_bracket_begin_shard": (i32, [vp, i32, C.c_double, i32]),
+        "ffb_bracket_phase1_finish": (i32, [vp, i32p, i32p, i32p, f32p, f32p, u8p]),
+        "ffb_bracket_radial": (i32, [vp, i32p, i32p, i32, i32, f64p, f64p]),
         "ffb_bracket_push": (i32, [vp, vp, i32, sz, sz]),
         "ffb_bracket_finish": (i32, [vp, i32p, f64p, u8p, i32p, i32p, f32p, f32p, f64p]),
         "ffb_sync": (i32, [vp]),
@@ -169,7 +174,6 @@ class FlowContext:
             raise FFBError(rc, (self._lib.ffb_last_error(None) or b"").decode())
         self._h = h
         self.device = device
-        self.geometry = None
 
     # -- plumbing
     def _ck(self, rc: int):
@@ -195,13 +199,58 @@ class FlowContext:
 
     # -- geometry / bracket API
     def configure(self, width: int, height: int, batch_frames: int = 16, max_bracket_pairs: int = 4096):
-        geo = (int(width), int(height), int(batch_frames), int(max_bracket_pairs))
-        if geo != self.geometry:
-            self._ck(self._lib.ffb_configure(self._h, *geo))
-            self.geometry = geo
+        """Incremental on the C side: unchanged or smaller requests touch nothing on the device."""
+        self._ck(self._lib.ffb_configure(self._h, int(width), int(height), int(batch_frames), int(max_bracket_pairs)))
+
+    @property
+    def geometry(self):
+        """(width, height, batch_frames, max_bracket_pairs) of the last successful configure, None before it."""
+        v = [C.c_int32(0) for _ in range(4)]
+        self._ck(self._lib.ffb_get_geometry(self._h, *(C.byref(x) for x in v)))
+        geo = tuple(int(x.value) for x in v)
+        return geo if geo[0] > 0 else None
+
+    def alloc_counts(self):
+        """(cudaMalloc calls, cudaHostAlloc calls) made for this context so far."""
+        d, h = C.c_int64(0), C.c_int64(0)
+        self._ck(self._lib.ffb_alloc_counts(self._h, C.byref(d), C.byref(h)))
+        return int(d.value), int(h.value)
 
     def bracket_begin(self, pov_mode: bool = False, cut_threshold: float = 7.0):
         self._ck(self._lib.ffb_bracket_begin(self._h, int(bool(pov_mode)), float(cut_threshold)))
+
+    # -- frame-range shard of a bracket: phase 1 (flows, raw centres, cut test), exchange of the raw centres
+    #    with the neighbouring shards on the host, phase 2 (radial scalars)
+    def bracket_begin_shard(self, shard_pairs: int, pov_mode: bool = False, cut_threshold: float = 7.0):
+        self._ck(self._lib.ffb_bracket_begin_shard(self._h, int(bool(pov_mode)), float(cut_threshold), int(shard_pairs)))
+
+    def bracket_phase1_finish(self):
+        m = self.geometry[3]
+        out = dict(cx=np.empty(m, np.int32), cy=np.empty(m, np.int32), val=np.empty(m, np.float32),
+                   mean_mag=np.empty(m, np.float32), cut=np.empty(m, np.uint8))
+        n = C.c_int32(0)
+        i32p = C.POINTER(C.c_int32)
+        self._ck(self._lib.ffb_bracket_phase1_finish(self._h, C.byref(n), out["cx"].ctypes.data_as(i32p),
+                                                     out["cy"].ctypes.data_as(i32p), _f32(out["val"]), _f32(out["mean_mag"]),
+                                                     _u8(out["cut"])))
+        k = n.value
+        res = {key: v[:k].copy() for key, v in out.items()}
+        res["cut"] = res["cut"].astype(bool)
+        res["n_pairs"] = k
+        return res
+
+    def bracket_radial(self, cx_ext, cy_ext, first: int, n_pairs: int):
+        """cx_ext / cy_ext: raw centres of the shard's pairs and of up to 6 neighbours on each side (clipped to the
+        bracket), the shard's first pair at index `first`.  Returns (scalar f64[n], centers f64[n, 2])."""
+        cx_ext = np.ascontiguousarray(cx_ext, np.int32)
+        cy_ext = np.ascontiguousarray(cy_ext, np.int32)
+        assert cx_ext.shape == cy_ext.shape and cx_ext.ndim == 1
+        scalar = np.empty(max(n_pairs, 1), np.float64)
+        centers = np.empty((max(n_pairs, 1), 2), np.float64)
+        i32p, f64p = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+        self._ck(self._lib.ffb_bracket_radial(self._h, cx_ext.ctypes.data_as(i32p), cy_ext.ctypes.data_as(i32p), int(cx_ext.size),
+                                              int(first), scalar.ctypes.data_as(f64p), centers.ctypes.data_as(f64p)))
+        return scalar[:n_pairs].copy(), centers[:n_pairs].copy()
 
     def bracket_push(self, frames: np.ndarray):
         """frames: uint8 [n, H, W] (or [H, W]); the last axis must be contiguous."""
@@ -291,7 +340,6 @@ class FlowContext:
         h, w = prev.shape
         out = np.empty((h, w, 2), np.float32)
         self._ck(self._lib.ffb_farneback(self._h, _u8(prev), _u8(nxt), w, h, w, _f32(out)))
-        self.geometry = None   # per-call functions may re-configure the context
         return out
 
     def max_divergence(self, flow: np.ndarray):
@@ -299,7 +347,6 @@ class FlowContext:
         h, w = flow.shape[:2]
         x, y, v = C.c_int32(), C.c_int32(), C.c_float()
         self._ck(self._lib.ffb_max_divergence(self._h, _f32(flow), w, h, C.byref(x), C.byref(y), C.byref(v)))
-        self.geometry = None
         return x.value, y.value, np.float32(v.value)
 
     def mean_magnitude(self, flow: np.ndarray) -> np.float32:
@@ -307,7 +354,6 @@ class FlowContext:
         h, w = flow.shape[:2]
         v = C.c_float()
         self._ck(self._lib.ffb_mean_magnitude(self._h, _f32(flow), w, h, C.byref(v)))
-        self.geometry = None
         return np.float32(v.value)
 
     def radial_motion(self, flow: np.ndarray, center, is_cut: bool, pov_mode: bool = False) -> float:
@@ -316,7 +362,6 @@ class FlowContext:
         v = C.c_double()
         self._ck(self._lib.ffb_radial_motion(self._h, _f32(flow), w, h, float(center[0]), float(center[1]),
                                              int(bool(is_cut)), int(bool(pov_mode)), C.byref(v)))
-        self.geometry = None
         return float(v.value)
 
     # -- stage hooks

@@ -176,6 +176,7 @@ struct Level {
 };
 
 struct ProfRec { int kid; int level; double bytes; cudaEvent_t e0, e1; };
+typedef int PtrKindTag;
 
 }  // namespace
 
@@ -193,6 +194,8 @@ struct ffb_ctx {
     FfbPolyConsts poly;
     // geometry
     int W = 0, H = 0, B = 0, maxPairs = 0, nlev = 0, S = 0, ring_n = 0, fp0 = 0;
+    int Bcap = 0, pairsCap = 0;                 // allocated capacities (B / maxPairs are the limits of the last ffb_configure)
+    int64_t n_dev_alloc = 0, n_host_alloc = 0;  // cudaMalloc / cudaHostAlloc calls made for this context so far
     bool pyr_fast = false;
     Level lev[FFB_MAX_LEVELS];
     float* R = nullptr;
@@ -204,6 +207,7 @@ struct ffb_ctx {
     uint8_t* h_pin[2] = {nullptr, nullptr};
     // per-bracket results (device) + partials
     int *d_cx = nullptr, *d_cy = nullptr;
+    int *d_cx_ext = nullptr, *d_cy_ext = nullptr;   // raw centres handed in by ffb_bracket_radial (shard + 6 each side)
     float *d_val = nullptr, *d_mm = nullptr;
     unsigned char* d_cut = nullptr;
     double *d_centers = nullptr, *d_scalar = nullptr;
@@ -226,6 +230,10 @@ struct ffb_ctx {
     int pov = 0;
     float thr = 7.f;
     int frames_seen = 0, pairs_done = 0, radial_done = 0, batch_no = 0;
+    bool deferred = false;      // shard mode: the radial pass waits for ffb_bracket_radial (external raw centres)
+    bool phase1_read = false;   // ffb_bracket_phase1_finish has been called for the open bracket
+    int pend = 0;               // pre-processed gray frames waiting in d_u8[batch_no & 1] for a full batch
+    PtrKindTag pend_kind = 0;   // source kind of the colour frames they came from (first-batch policy)
     // instrumentation
     bool prof = false;
     std::vector<ProfRec> recs;
@@ -284,6 +292,7 @@ int dev_alloc(ffb_ctx* c, T** p, size_t count) {
     void* v = nullptr;
     cudaError_t e = cudaMalloc(&v, count * sizeof(T) + 256);   // +256: vector loads may touch a row's tail
     if (e != cudaSuccess) return fail(c, FFB_E_NOMEM, "cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+    if (c) c->n_dev_alloc++;
     *p = (T*)v;
     return FFB_OK;
 }
@@ -533,12 +542,27 @@ int launch_flow_iter(ffb_ctx* c, FfbRing R, size_t plane, int rp, int w, int h, 
     const IterCfg k = iter_cfg();
     int nt = k.nt, u = k.u, ho = k.ho;
     if (k.cnt > 0 && c->cur_level >= 2) { nt = k.cnt; u = k.cu; ho = k.cho; }
+    if (c->cur_level >= 0 && c->cur_level < FFB_MAX_LEVELS) {      // FFB_ITER_CFG_K<k>: one level only
+        char name[24];
+        snprintf(name, sizeof(name), "FFB_ITER_CFG_K%d", c->cur_level);
+        if (const char* e = getenv(name)) {
+            int a1 = 0, a2 = 0, a3 = 0;
+            if (sscanf(e, "%dx%dx%d", &a1, &a2, &a3) == 3) { nt = a1; u = a2; ho = a3; }
+        }
+    }
     if (nt == 0) {
-        // Frames under 1280x720 (the reference's 256x256 product mode, 640x360): 160-thread strips of up to 144 outputs, so a
-        // 256-column level is 2 strips instead of 3 and a 128-column level 1 instead of 2: +10 % at 256x256; at 1080p the
-        // same variant loses 3 % (3 CTAs / SM), so large frames keep 128 threads (profiles/r1_sweep_segments.txt).
+        // Defaults from the round-2 sweeps on a B200 (profiles/r2_sweep_flow_iter.txt), keyed on the frame the context
+        // is configured for (never on the batch):
+        //   1280x720 and larger   256 threads, 4 rows per step, 8 outputs per horizontal task: 242-column strips carry
+        //                         5.5 % halo columns instead of 10.9 %, and the 120 horizontal tasks of a step fill 4 of
+        //                         the 8 warps (1080p: +8.4 % over 128x2x4, 4K: +7 %)
+        //   up to 320 columns     160 threads x 2 rows x 4 outputs (the reference's 256x256 product mode: 2 strips)
+        //   in between            128 threads x 2 rows x 4 outputs (640x360: +8 % over 160x2x4)
         const long long frame_px = c->seg_frame_px > 0 ? c->seg_frame_px : (long long)w * h;
-        nt = frame_px < 1280LL * 720 ? 160 : 128;
+        const int frame_w = c->seg_frame_px > 0 ? c->W : w;
+        if (frame_px >= 1280LL * 720) { nt = 256; u = 4; ho = 8; }
+        else if (frame_w <= 320) { nt = 160; u = 2; ho = 4; }
+        else { nt = 128; u = 2; ho = 4; }
     }
     switch (nt * 100 + u * 10 + ho) {
         case 12824:
@@ -556,6 +580,10 @@ int launch_flow_iter(ffb_ctx* c, FfbRing R, size_t plane, int rp, int w, int h, 
         case 25624: return launch_flow_iter_t<256, 2, 2, 4>(c, a, npairs, k.sh, bytes);
         case 25628: return launch_flow_iter_t<256, 2, 2, 8>(c, a, npairs, k.sh, bytes);
         case 25648: return launch_flow_iter_t<256, 4, 2, 8>(c, a, npairs, k.sh, bytes);
+        case 25644: return launch_flow_iter_t<256, 4, 2, 4>(c, a, npairs, k.sh, bytes);
+        case 51248: return launch_flow_iter_t<512, 4, 1, 8>(c, a, npairs, k.sh, bytes);
+        case 51224: return launch_flow_iter_t<512, 2, 1, 4>(c, a, npairs, k.sh, bytes);
+        case 19248: return launch_flow_iter_t<192, 4, 2, 8>(c, a, npairs, k.sh, bytes);
         case 9624:  return launch_flow_iter_t<96, 2, 5, 4>(c, a, npairs, k.sh, bytes);
         default: break;
     }
@@ -563,25 +591,57 @@ int launch_flow_iter(ffb_ctx* c, FfbRing R, size_t plane, int rp, int w, int h, 
 }
 
 // ------------------------------------------------------------------ geometry
-void free_geometry(ffb_ctx* c) {
+// Device / pinned memory comes in four groups with their own lifetimes, so that ffb_configure only
+// re-allocates what a request outgrows:
+//   frame size   level tables (freed when width or height change, together with everything below)
+//   batch        level images, flow ping-pong, expansion ring, frame staging     capacity Bcap frames
+//   flow ring    final-flow ring and the reduction partials indexed by ring slot  capacity ring_n pairs
+//   pairs        per-pair results and their pinned staging                        capacity pairsCap pairs
+void free_batch_group(ffb_ctx* c) {
     for (int l = 0; l < FFB_MAX_LEVELS; ++l) {
         Level& L = c->lev[l];
-        dev_free(L.xi); dev_free(L.yi); dev_free(L.uxi); dev_free(L.uyi);
-        dev_free(L.xa); dev_free(L.ya); dev_free(L.uxa); dev_free(L.uya);
         dev_free(L.I); dev_free(L.fA); dev_free(L.fB);
-        L = Level();
     }
-    dev_free(c->R); dev_free(c->ring);
+    dev_free(c->R);
     for (int b = 0; b < 2; ++b) {
         dev_free(c->d_u8[b]);
         if (c->h_pin[b]) cudaFreeHost(c->h_pin[b]);
         c->h_pin[b] = nullptr;
     }
+    c->Bcap = 0;
+    c->S = 0;
+}
+void free_ring_group(ffb_ctx* c) {
+    dev_free(c->ring); dev_free(c->d_pkey); dev_free(c->d_psum); dev_free(c->d_rpart);
+    c->ring_n = 0;
+}
+void free_pairs_group(ffb_ctx* c) {
     dev_free(c->d_cx); dev_free(c->d_cy); dev_free(c->d_val); dev_free(c->d_mm); dev_free(c->d_cut);
-    dev_free(c->d_centers); dev_free(c->d_scalar); dev_free(c->d_pkey); dev_free(c->d_psum); dev_free(c->d_rpart);
+    dev_free(c->d_centers); dev_free(c->d_scalar); dev_free(c->d_cx_ext); dev_free(c->d_cy_ext);
     if (c->h_res) cudaFreeHost(c->h_res);
     c->h_res = nullptr;
+    c->pairsCap = 0;
+}
+void free_geometry(ffb_ctx* c) {
+    free_batch_group(c);
+    free_ring_group(c);
+    free_pairs_group(c);
+    for (int l = 0; l < FFB_MAX_LEVELS; ++l) {
+        Level& L = c->lev[l];
+        dev_free(L.xi); dev_free(L.yi); dev_free(L.uxi); dev_free(L.uyi);
+        dev_free(L.xa); dev_free(L.ya); dev_free(L.uxa); dev_free(L.uya);
+        L = Level();
+    }
     c->W = c->H = c->B = c->maxPairs = c->nlev = 0;
+}
+
+int host_alloc(ffb_ctx* c, void** p, size_t bytes) {
+    if (cudaHostAlloc(p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(c, FFB_E_NOMEM, "cudaHostAlloc(%zu) failed", bytes);
+    }
+    c->n_host_alloc++;
+    return FFB_OK;
 }
 
 int build_level_tables(ffb_ctx* c, Level& L, int W, int H, int wc, int hc) {
@@ -604,66 +664,99 @@ int build_level_tables(ffb_ctx* c, Level& L, int W, int H, int wc, int hc) {
 
 bool pyramid_fast_ok(int W, int H, const LevelPlan& p);
 
-int configure(ffb_ctx* c, int W, int H, int B, int maxPairs) {
-    if (W < 16 || H < 16 || B < 1 || maxPairs < 1 || (double)W * H >= 4294967295.0)
-        return fail(c, FFB_E_INVALID, "ffb_configure: bad geometry %dx%d batch %d pairs %d", W, H, B, maxPairs);
-    if (c->in_bracket) return fail(c, FFB_E_INVALID, "ffb_configure inside a bracket");
+int quiesce(ffb_ctx* c) {
     CK(c, cudaStreamSynchronize(c->s_comp));
     CK(c, cudaStreamSynchronize(c->s_copy));
-    free_geometry(c);
-    const LevelPlan p = make_plan(W, H);
-    c->W = W; c->H = H; c->B = B; c->maxPairs = maxPairs; c->nlev = p.n;
-    c->pyr_fast = pyramid_fast_ok(W, H, p);
-    c->S = B + 2;      // the first batch of a bracket may carry B + 1 frames (= B pairs)
-    c->ring_n = B + 8;
-    size_t off = 0;
-    for (int l = 0; l < p.n; ++l) {
-        Level& L = c->lev[l];
-        L.k = p.k[l]; L.w = p.w[l]; L.h = p.h[l]; L.ksize = p.ksize[l]; L.sigma = p.sigma[l];
-        L.rp = ffb_round_up(L.w, 4);
-        L.plane = (size_t)L.rp * L.h;
-        L.fp = ffb_round_up(L.w, 4);
-        L.r_off = off;
-        off += 5 * L.plane;
-        off = (off + 63) / 64 * 64;
-        L.taps = make_taps(L.ksize, L.sigma);
-        TRY(build_level_tables(c, L, W, H, l > 0 ? c->lev[l - 1].w : 0, l > 0 ? c->lev[l - 1].h : 0));
-        TRY(dev_alloc(c, &L.I, (size_t)(B + 1) * L.plane));
-        TRY(dev_alloc(c, &L.fA, (size_t)B * L.fp * L.h));
-        TRY(dev_alloc(c, &L.fB, (size_t)B * L.fp * L.h));
+    for (int i = 0; i < 3; ++i) CK(c, cudaStreamSynchronize(c->s_aux[i]));
+    return FFB_OK;
+}
+
+// ring_pairs: final flows that must stay resident at once (0 = the streaming minimum, batch + 8)
+int configure(ffb_ctx* c, int W, int H, int B, int maxPairs, int ring_pairs = 0) {
+    // arguments are checked before anything is touched: a refused call leaves the configuration as it was
+    if (W < 16 || H < 16 || B < 1 || maxPairs < 1 || ring_pairs < 0 || (double)W * H >= 4294967295.0)
+        return fail(c, FFB_E_INVALID, "ffb_configure: bad geometry %dx%d batch %d pairs %d", W, H, B, maxPairs);
+    if (c->in_bracket) return fail(c, FFB_E_INVALID, "ffb_configure inside a bracket");
+    const int need_ring = ring_pairs > B + 8 ? ring_pairs : B + 8;
+    const bool new_frame = W != c->W || H != c->H;
+    if (!new_frame && B <= c->Bcap && need_ring <= c->ring_n && maxPairs <= c->pairsCap) {
+        c->B = B;                 // logical limits; the capacities stay
+        c->maxPairs = maxPairs;
+        return FFB_OK;
     }
-    c->r_slot_floats = (off + 127) / 128 * 128;      // 512-byte multiples
-    TRY(dev_alloc(c, &c->R, (size_t)c->S * c->r_slot_floats));
-    c->fp0 = c->lev[p.n - 1].fp;
-    c->ring_stride = (size_t)c->fp0 * H;
-    TRY(dev_alloc(c, &c->ring, (size_t)c->ring_n * c->ring_stride));
-    const size_t fbytes = (size_t)W * H;
-    for (int b = 0; b < 2; ++b) {
-        TRY(dev_alloc(c, &c->d_u8[b], (size_t)(B + 1) * fbytes));
-        void* hp = nullptr;
-        if (cudaHostAlloc(&hp, (size_t)(B + 1) * fbytes, cudaHostAllocDefault) != cudaSuccess)
-            return fail(c, FFB_E_NOMEM, "cudaHostAlloc(%zu) failed", (size_t)(B + 1) * fbytes);
-        c->h_pin[b] = (uint8_t*)hp;
+    TRY(quiesce(c));
+    if (new_frame) {
+        free_geometry(c);
+        const LevelPlan p = make_plan(W, H);
+        c->W = W; c->H = H; c->nlev = p.n;
+        c->pyr_fast = pyramid_fast_ok(W, H, p);
+        size_t off = 0;
+        for (int l = 0; l < p.n; ++l) {
+            Level& L = c->lev[l];
+            L.k = p.k[l]; L.w = p.w[l]; L.h = p.h[l]; L.ksize = p.ksize[l]; L.sigma = p.sigma[l];
+            L.rp = ffb_round_up(L.w, 4);
+            L.plane = (size_t)L.rp * L.h;
+            L.fp = ffb_round_up(L.w, 4);
+            L.r_off = off;
+            off += 5 * L.plane;
+            off = (off + 63) / 64 * 64;
+            L.taps = make_taps(L.ksize, L.sigma);
+            TRY(build_level_tables(c, L, W, H, l > 0 ? c->lev[l - 1].w : 0, l > 0 ? c->lev[l - 1].h : 0));
+        }
+        c->r_slot_floats = (off + 127) / 128 * 128;      // 512-byte multiples
+        c->fp0 = c->lev[p.n - 1].fp;
+        c->ring_stride = (size_t)c->fp0 * H;
+        // reduction geometry: fixed per frame size so results do not depend on batch composition
+        c->div_rpb = 8;       // whole rows per block: long contiguous reads (a column-marching variant measured slower)
+        c->div_gx = (H + c->div_rpb - 1) / c->div_rpb;
+        c->div_gy = 1;
+        c->div_nblk = c->div_gx;
+        c->rad_gx = (W + 255) / 256;
+        c->rad_rpb = 32;
+        c->rad_gy = (H + c->rad_rpb - 1) / c->rad_rpb;
     }
-    TRY(dev_alloc(c, &c->d_cx, (size_t)maxPairs)); TRY(dev_alloc(c, &c->d_cy, (size_t)maxPairs));
-    TRY(dev_alloc(c, &c->d_val, (size_t)maxPairs)); TRY(dev_alloc(c, &c->d_mm, (size_t)maxPairs));
-    TRY(dev_alloc(c, &c->d_cut, (size_t)maxPairs));
-    TRY(dev_alloc(c, &c->d_centers, (size_t)2 * maxPairs)); TRY(dev_alloc(c, &c->d_scalar, (size_t)maxPairs));
-    // reduction geometry: fixed per configuration so results do not depend on batch composition
-    c->div_rpb = 8;       // whole rows per block: long contiguous reads (a column-marching variant measured slower)
-    c->div_gx = (H + c->div_rpb - 1) / c->div_rpb;
-    c->div_gy = 1;
-    c->div_nblk = c->div_gx;
-    c->rad_gx = (W + 255) / 256;
-    c->rad_rpb = 32;
-    c->rad_gy = (H + c->rad_rpb - 1) / c->rad_rpb;
-    TRY(dev_alloc(c, &c->d_pkey, (size_t)c->ring_n * c->div_nblk));
-    TRY(dev_alloc(c, &c->d_psum, (size_t)c->ring_n * c->div_nblk));
-    TRY(dev_alloc(c, &c->d_rpart, (size_t)c->ring_n * c->rad_gx * c->rad_gy));
-    void* hr = nullptr;
-    if (cudaHostAlloc(&hr, (size_t)maxPairs * 48 + 256, cudaHostAllocDefault) != cudaSuccess)
-        return fail(c, FFB_E_NOMEM, "cudaHostAlloc(results) failed");
-    c->h_res = (char*)hr;
+    if (B > c->Bcap) {
+        free_batch_group(c);
+        for (int l = 0; l < c->nlev; ++l) {
+            Level& L = c->lev[l];
+            TRY(dev_alloc(c, &L.I, (size_t)(B + 1) * L.plane));
+            TRY(dev_alloc(c, &L.fA, (size_t)B * L.fp * L.h));
+            TRY(dev_alloc(c, &L.fB, (size_t)B * L.fp * L.h));
+        }
+        c->S = B + 2;      // the first batch of a bracket may carry B + 1 frames (= B pairs)
+        TRY(dev_alloc(c, &c->R, (size_t)c->S * c->r_slot_floats));
+        const size_t fbytes = (size_t)W * H;
+        for (int b = 0; b < 2; ++b) {
+            TRY(dev_alloc(c, &c->d_u8[b], (size_t)(B + 1) * fbytes));
+            void* hp = nullptr;
+            TRY(host_alloc(c, &hp, (size_t)(B + 1) * fbytes));
+            c->h_pin[b] = (uint8_t*)hp;
+        }
+        c->Bcap = B;
+    }
+    if (need_ring > c->ring_n) {
+        free_ring_group(c);
+        TRY(dev_alloc(c, &c->ring, (size_t)need_ring * c->ring_stride));
+        TRY(dev_alloc(c, &c->d_pkey, (size_t)need_ring * c->div_nblk));
+        TRY(dev_alloc(c, &c->d_psum, (size_t)need_ring * c->div_nblk));
+        TRY(dev_alloc(c, &c->d_rpart, (size_t)need_ring * c->rad_gx * c->rad_gy));
+        c->ring_n = need_ring;
+    }
+    if (maxPairs > c->pairsCap) {
+        free_pairs_group(c);
+        const size_t m = (size_t)maxPairs;
+        TRY(dev_alloc(c, &c->d_cx, m)); TRY(dev_alloc(c, &c->d_cy, m));
+        TRY(dev_alloc(c, &c->d_val, m)); TRY(dev_alloc(c, &c->d_mm, m));
+        TRY(dev_alloc(c, &c->d_cut, m));
+        TRY(dev_alloc(c, &c->d_centers, 2 * m)); TRY(dev_alloc(c, &c->d_scalar, m));
+        TRY(dev_alloc(c, &c->d_cx_ext, m + 12)); TRY(dev_alloc(c, &c->d_cy_ext, m + 12));
+        void* hr = nullptr;
+        TRY(host_alloc(c, &hr, m * 48 + 256));
+        c->h_res = (char*)hr;
+        c->pairsCap = maxPairs;
+    }
+    c->B = B;
+    c->maxPairs = maxPairs;
     return FFB_OK;
 }
 
@@ -855,15 +948,18 @@ int phase1_reduce(ffb_ctx* c, int p0, int np) {
     return launch_phase1_finish(c, p0, np);
 }
 
-// radial pass for bracket pairs [j0, j1); n = number of pairs known so far (window truncation)
-int radial_range(ffb_ctx* c, int j0, int j1, int n) {
+// radial pass for bracket pairs [j0, j1); n = number of pairs known so far (window truncation).
+// smooth = false: d_centers already holds the centres of these pairs (ffb_bracket_radial)
+int radial_range(ffb_ctx* c, int j0, int j1, int n, bool smooth = true) {
     while (j0 < j1) {
         const int cnt = (j1 - j0 < c->ring_n) ? j1 - j0 : c->ring_n;
-        prof_begin(c, FFB_K_SMALL, 0);
-        FFB_LAUNCH(k_smooth_centers, dim3((cnt + 127) / 128), dim3(128), 0, c->s_comp, c->d_cx, c->d_cy, n, j0,
-                   j0 + cnt, c->d_centers);
-        prof_end(c);
-        CKL(c);
+        if (smooth) {
+            prof_begin(c, FFB_K_SMALL, 0);
+            FFB_LAUNCH(k_smooth_centers, dim3((cnt + 127) / 128), dim3(128), 0, c->s_comp, c->d_cx, c->d_cy, n, j0,
+                       j0 + cnt, 0, c->d_centers);
+            prof_end(c);
+            CKL(c);
+        }
         FfbRadArgs r;
         r.flow = FfbRing{(char*)c->ring, c->ring_stride * sizeof(float2), j0 % c->ring_n, c->ring_n};
         r.fp = c->fp0; r.w = c->W; r.h = c->H; r.rows_per_block = c->rad_rpb;
@@ -932,12 +1028,14 @@ int process_batch(ffb_ctx* c, const uint8_t* frames, int nb, size_t pitch, size_
     if (np > 0) {
         const int p0 = c->pairs_done;
         if (p0 + np > c->maxPairs) return fail(c, FFB_E_INVALID, "bracket exceeds max_bracket_pairs=%d", c->maxPairs);
+        if (c->deferred && p0 + np > c->ring_n)
+            return fail(c, FFB_E_INVALID, "shard exceeds the %d pairs announced to ffb_bracket_begin_shard", c->ring_n);
         TRY(flow_pairs(c, p0, np));
         if (c->sliced_divmag) TRY(launch_phase1_finish(c, p0, np));
         else TRY(phase1_reduce(c, p0, np));
         c->pairs_done += np;
         const int r1 = c->pairs_done - 6;
-        if (r1 > c->radial_done) {
+        if (!c->deferred && r1 > c->radial_done) {
             TRY(radial_range(c, c->radial_done, r1, c->pairs_done));
             c->radial_done = r1;
         }
@@ -1140,25 +1238,64 @@ int ffb_host_alloc(void** p, size_t bytes) {
 }
 int ffb_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? FFB_OK : FFB_E_CUDA; }
 
-int ffb_configure(ffb_ctx* c, int w, int h, int batch_frames, int max_pairs) {
+static int configure_checked(ffb_ctx* c, int w, int h, int batch_frames, int max_pairs, int ring_pairs) {
     if (!c) return FFB_E_INVALID;
     CK(c, cudaSetDevice(c->device));
-    const int rc = configure(c, w, h, batch_frames, max_pairs);
-    if (rc != FFB_OK && !c->in_bracket) {   // leave no half-allocated geometry behind
+    const int W0 = c->W;
+    const int rc = configure(c, w, h, batch_frames, max_pairs, ring_pairs);
+    // an allocation that failed half-way leaves no half-built geometry behind (argument errors change nothing)
+    if (rc != FFB_OK && rc != FFB_E_INVALID && !c->in_bracket) {
         const std::string msg = c->err;
         free_geometry(c);
         c->err = msg;
     }
+    (void)W0;
     return rc;
+}
+
+int ffb_configure(ffb_ctx* c, int w, int h, int batch_frames, int max_pairs) {
+    return configure_checked(c, w, h, batch_frames, max_pairs, 0);
+}
+
+int ffb_get_geometry(const ffb_ctx* c, int* w, int* h, int* batch_frames, int* max_pairs) {
+    if (!c) return FFB_E_INVALID;
+    if (w) *w = c->W;
+    if (h) *h = c->H;
+    if (batch_frames) *batch_frames = c->B;
+    if (max_pairs) *max_pairs = c->maxPairs;
+    return FFB_OK;
+}
+
+int ffb_alloc_counts(const ffb_ctx* c, int64_t* device_allocs, int64_t* host_allocs) {
+    if (!c) return FFB_E_INVALID;
+    if (device_allocs) *device_allocs = c->n_dev_alloc;
+    if (host_allocs) *host_allocs = c->n_host_alloc;
+    return FFB_OK;
 }
 
 int ffb_bracket_begin(ffb_ctx* c, int pov, double thr) {
     if (!c || c->W == 0) return fail(c, FFB_E_INVALID, "ffb_bracket_begin before ffb_configure");
+    if (c->in_bracket) return fail(c, FFB_E_INVALID, "ffb_bracket_begin inside a bracket (finish or abort it first)");
     CK(c, cudaSetDevice(c->device));
     c->in_bracket = true;
+    c->deferred = false;
+    c->phase1_read = false;
+    c->pend = 0;
     c->pov = pov ? 1 : 0;
     c->thr = (float)thr;
     c->frames_seen = c->pairs_done = c->radial_done = 0;
+    return FFB_OK;
+}
+
+int ffb_bracket_begin_shard(ffb_ctx* c, int pov, double thr, int shard_pairs) {
+    if (!c || c->W == 0) return fail(c, FFB_E_INVALID, "ffb_bracket_begin_shard before ffb_configure");
+    if (c->in_bracket) return fail(c, FFB_E_INVALID, "ffb_bracket_begin_shard inside a bracket (finish or abort it first)");
+    if (shard_pairs < 1) return fail(c, FFB_E_INVALID, "ffb_bracket_begin_shard: shard_pairs must be >= 1");
+    // every final flow of the shard stays resident until the centres of its neighbours are known
+    const int pairs = c->maxPairs > shard_pairs ? c->maxPairs : shard_pairs;
+    TRY(configure_checked(c, c->W, c->H, c->B, pairs, shard_pairs));
+    TRY(ffb_bracket_begin(c, pov, thr));
+    c->deferred = true;
     return FFB_OK;
 }
 
@@ -1174,10 +1311,21 @@ static int batch_cap(const ffb_ctx* c, PtrKind kind) {
     return c->B + 1;
 }
 
+// ffb_bracket_push_bgr gathers pre-processed gray frames in the device staging buffer until a batch is full;
+// whatever is waiting there runs as a (short) batch before results are read or gray frames are pushed directly
+static int flush_pending(ffb_ctx* c) {
+    if (c->pend <= 0) return FFB_OK;
+    const int nb = c->pend;
+    c->pend = 0;
+    return process_batch(c, c->d_u8[c->batch_no & 1], nb, (size_t)c->W, (size_t)c->W * c->H, PTR_DEVICE);
+}
+
 int ffb_bracket_push(ffb_ctx* c, const uint8_t* frames, int n, size_t pitch, size_t stride) {
     if (!c || !c->in_bracket) return fail(c, FFB_E_INVALID, "ffb_bracket_push outside a bracket");
+    if (c->phase1_read) return fail(c, FFB_E_INVALID, "ffb_bracket_push after ffb_bracket_phase1_finish");
     if (!frames || n < 0 || pitch < (size_t)c->W || stride < pitch * (size_t)(c->H - 1) + c->W)
         return fail(c, FFB_E_INVALID, "ffb_bracket_push: bad arguments");
+    TRY(flush_pending(c));
     const PtrKind kind = classify(frames);
     for (int i = 0; i < n;) {
         const int cap = batch_cap(c, kind);
@@ -1198,6 +1346,8 @@ int ffb_bracket_abort(ffb_ctx* c) {
     for (int i = 0; i < 3; ++i) cudaStreamSynchronize(c->s_aux[i]);
     cudaGetLastError();
     c->in_bracket = false;
+    c->deferred = c->phase1_read = false;
+    c->pend = 0;
     c->frames_seen = c->pairs_done = c->radial_done = 0;
     return FFB_OK;
 }
@@ -1209,16 +1359,10 @@ int ffb_sync(ffb_ctx* c) {
     return FFB_OK;
 }
 
-int ffb_bracket_finish(ffb_ctx* c, int* n_pairs, double* scalar, uint8_t* cut, int32_t* cx, int32_t* cy, float* val,
-                       float* mean_mag, double* centers) {
-    if (!c || !c->in_bracket) return fail(c, FFB_E_INVALID, "ffb_bracket_finish outside a bracket");
-    const int n = c->pairs_done;
-    if (n > c->radial_done) {
-        TRY(radial_range(c, c->radial_done, n, n));
-        c->radial_done = n;
-    }
-    c->in_bracket = false;
-    if (n_pairs) *n_pairs = n;
+// D2H of the per-pair results of the open bracket (each output may be NULL) through the pinned staging
+// buffer, then a wait for both streams.  with_radial: scalar and centers are valid.
+static int fetch_results(ffb_ctx* c, int n, bool with_radial, double* scalar, uint8_t* cut, int32_t* cx, int32_t* cy, float* val,
+                         float* mean_mag, double* centers) {
     if (n > 0) {
         char* h = c->h_res;
         size_t o = 0;
@@ -1229,16 +1373,18 @@ int ffb_bracket_finish(ffb_ctx* c, int* n_pairs, double* scalar, uint8_t* cut, i
         float* h_val = (float*)(h + o); o += (size_t)n * 4;
         float* h_mm = (float*)(h + o); o += (size_t)n * 4;
         unsigned char* h_cut = (unsigned char*)(h + o);
-        CK(c, cudaMemcpyAsync(h_scalar, c->d_scalar, (size_t)n * 8, cudaMemcpyDeviceToHost, c->s_comp));
-        CK(c, cudaMemcpyAsync(h_centers, c->d_centers, (size_t)n * 16, cudaMemcpyDeviceToHost, c->s_comp));
+        if (with_radial) {
+            CK(c, cudaMemcpyAsync(h_scalar, c->d_scalar, (size_t)n * 8, cudaMemcpyDeviceToHost, c->s_comp));
+            CK(c, cudaMemcpyAsync(h_centers, c->d_centers, (size_t)n * 16, cudaMemcpyDeviceToHost, c->s_comp));
+        }
         CK(c, cudaMemcpyAsync(h_cx, c->d_cx, (size_t)n * 4, cudaMemcpyDeviceToHost, c->s_comp));
         CK(c, cudaMemcpyAsync(h_cy, c->d_cy, (size_t)n * 4, cudaMemcpyDeviceToHost, c->s_comp));
         CK(c, cudaMemcpyAsync(h_val, c->d_val, (size_t)n * 4, cudaMemcpyDeviceToHost, c->s_comp));
         CK(c, cudaMemcpyAsync(h_mm, c->d_mm, (size_t)n * 4, cudaMemcpyDeviceToHost, c->s_comp));
         CK(c, cudaMemcpyAsync(h_cut, c->d_cut, (size_t)n, cudaMemcpyDeviceToHost, c->s_comp));
         CK(c, cudaStreamSynchronize(c->s_comp));
-        if (scalar) memcpy(scalar, h_scalar, (size_t)n * 8);
-        if (centers) memcpy(centers, h_centers, (size_t)n * 16);
+        if (with_radial && scalar) memcpy(scalar, h_scalar, (size_t)n * 8);
+        if (with_radial && centers) memcpy(centers, h_centers, (size_t)n * 16);
         if (cx) memcpy(cx, h_cx, (size_t)n * 4);
         if (cy) memcpy(cy, h_cy, (size_t)n * 4);
         if (val) memcpy(val, h_val, (size_t)n * 4);
@@ -1249,6 +1395,55 @@ int ffb_bracket_finish(ffb_ctx* c, int* n_pairs, double* scalar, uint8_t* cut, i
     }
     CK(c, cudaStreamSynchronize(c->s_copy));
     return FFB_OK;
+}
+
+int ffb_bracket_finish(ffb_ctx* c, int* n_pairs, double* scalar, uint8_t* cut, int32_t* cx, int32_t* cy, float* val,
+                       float* mean_mag, double* centers) {
+    if (!c || !c->in_bracket) return fail(c, FFB_E_INVALID, "ffb_bracket_finish outside a bracket");
+    if (c->deferred) return fail(c, FFB_E_INVALID, "shard bracket: use ffb_bracket_phase1_finish + ffb_bracket_radial");
+    TRY(flush_pending(c));
+    const int n = c->pairs_done;
+    if (n > c->radial_done) {
+        TRY(radial_range(c, c->radial_done, n, n));
+        c->radial_done = n;
+    }
+    c->in_bracket = false;
+    if (n_pairs) *n_pairs = n;
+    return fetch_results(c, n, true, scalar, cut, cx, cy, val, mean_mag, centers);
+}
+
+int ffb_bracket_phase1_finish(ffb_ctx* c, int* n_pairs, int32_t* cx, int32_t* cy, float* val, float* mean_mag, uint8_t* cut) {
+    if (!c || !c->in_bracket || !c->deferred)
+        return fail(c, FFB_E_INVALID, "ffb_bracket_phase1_finish outside a bracket opened with ffb_bracket_begin_shard");
+    TRY(flush_pending(c));
+    c->phase1_read = true;
+    if (n_pairs) *n_pairs = c->pairs_done;
+    return fetch_results(c, c->pairs_done, false, nullptr, cut, cx, cy, val, mean_mag, nullptr);
+}
+
+int ffb_bracket_radial(ffb_ctx* c, const int32_t* cx_ext, const int32_t* cy_ext, int n_ext, int first, double* scalar,
+                       double* centers) {
+    if (!c || !c->in_bracket || !c->deferred || !c->phase1_read)
+        return fail(c, FFB_E_INVALID, "ffb_bracket_radial before ffb_bracket_phase1_finish");
+    const int n = c->pairs_done;
+    if (n > 0 && (!cx_ext || !cy_ext || first < 0 || first > 6 || n_ext < first + n || n_ext > first + n + 6))
+        return fail(c, FFB_E_INVALID, "ffb_bracket_radial: %d external centres with the shard's first pair at %d do not frame %d pairs",
+                    n_ext, first, n);
+    if (n > 0) {
+        // the raw centres of the shard and of up to 6 neighbours on each side, as the neighbours computed them
+        CK(c, cudaMemcpyAsync(c->d_cx_ext, cx_ext, (size_t)n_ext * 4, cudaMemcpyHostToDevice, c->s_comp));
+        CK(c, cudaMemcpyAsync(c->d_cy_ext, cy_ext, (size_t)n_ext * 4, cudaMemcpyHostToDevice, c->s_comp));
+        prof_begin(c, FFB_K_SMALL, 0);
+        FFB_LAUNCH(k_smooth_centers, dim3((n + 127) / 128), dim3(128), 0, c->s_comp, c->d_cx_ext, c->d_cy_ext, n_ext, first,
+                   first + n, first, c->d_centers);
+        prof_end(c);
+        CKL(c);
+        TRY(radial_range(c, 0, n, n, false));
+        c->radial_done = n;
+    }
+    c->in_bracket = false;
+    c->deferred = c->phase1_read = false;
+    return fetch_results(c, n, true, scalar, nullptr, nullptr, nullptr, nullptr, nullptr, centers);
 }
 
 int ffb_flow_ring_size(const ffb_ctx* c) { return c ? c->ring_n : 0; }
@@ -1520,8 +1715,7 @@ static int preprocess_configure_plan(ffb_ctx* c, const ffb_ctx::PrePlan& p) {
     for (int b = 0; b < 2; ++b) {
         TRY(dev_alloc(c, &c->d_color[b], cbytes));
         void* hp = nullptr;
-        if (cudaHostAlloc(&hp, cbytes, cudaHostAllocDefault) != cudaSuccess)
-            return fail(c, FFB_E_NOMEM, "cudaHostAlloc(%zu) failed", cbytes);
+        TRY(host_alloc(c, &hp, cbytes));
         c->h_color[b] = (uint8_t*)hp;
     }
     c->pre = p;
@@ -1539,6 +1733,7 @@ int ffb_preprocess_configure_window(ffb_ctx* c, int W, int H, int target_w, int 
 
 int ffb_bracket_push_bgr(ffb_ctx* c, const uint8_t* bgr, int n, size_t pitch, size_t stride) {
     if (!c || !c->in_bracket) return fail(c, FFB_E_INVALID, "ffb_bracket_push_bgr outside a bracket");
+    if (c->phase1_read) return fail(c, FFB_E_INVALID, "ffb_bracket_push_bgr after ffb_bracket_phase1_finish");
     const ffb_ctx::PrePlan& pp = c->pre;
     if (pp.W == 0) return fail(c, FFB_E_INVALID, "ffb_bracket_push_bgr before ffb_preprocess_configure");
     if (c->W != pp.OW || c->H != pp.OH)
@@ -1549,50 +1744,48 @@ int ffb_bracket_push_bgr(ffb_ctx* c, const uint8_t* bgr, int n, size_t pitch, si
         return fail(c, FFB_E_INVALID, "ffb_bracket_push_bgr: bad arguments");
     const PtrKind kind = classify(bgr);
     const size_t fbytes = row * pp.H;
+    // The gray frames gather in the device staging buffer of the next batch and run through the hot path once the
+    // batch is full, however the caller cuts its pushes (a decoder hands over chunks much smaller than the batches
+    // that fill the GPU at 256x256); ffb_bracket_finish runs what is left.
     for (int i = 0; i < n;) {
         const int cap = batch_cap(c, kind);
-        const int nb = n - i < cap ? n - i : cap;
         const int b = c->batch_no & 1;
-        for (int j = 0; j < nb; j += PRE_CHUNK) {
-            const int m = nb - j < PRE_CHUNK ? nb - j : PRE_CHUNK;
-            const uint8_t* src = bgr + (size_t)(i + j) * stride;
-            const uint8_t* dsrc = src;
-            size_t dstride = stride;
-            int dpitch = (int)pitch;
-            if (kind != PTR_DEVICE) {
-                const int cb = c->color_no & 1;
-                c->color_no++;
-                CK(c, cudaStreamWaitEvent(c->s_copy, c->ev_pre[cb], 0));      // kernel that last read d_color[cb]
-                if (kind == PTR_PAGEABLE) {
-                    CK(c, cudaEventSynchronize(c->ev_ch2d[cb]));              // DMA that last read h_color[cb]
-                    for (int f = 0; f < m; ++f) {
-                        const uint8_t* s0 = src + (size_t)f * stride;
-                        uint8_t* d0 = c->h_color[cb] + (size_t)f * fbytes;
-                        if (pitch == row) memcpy(d0, s0, fbytes);
-                        else for (int y = 0; y < pp.H; ++y) memcpy(d0 + (size_t)y * row, s0 + (size_t)y * pitch, row);
-                    }
-                    CK(c, cudaMemcpyAsync(c->d_color[cb], c->h_color[cb], (size_t)m * fbytes, cudaMemcpyHostToDevice, c->s_copy));
-                } else if (pitch == row && stride == fbytes) {
-                    CK(c, cudaMemcpyAsync(c->d_color[cb], src, (size_t)m * fbytes, cudaMemcpyHostToDevice, c->s_copy));
-                } else {
-                    for (int f = 0; f < m; ++f)
-                        CK(c, cudaMemcpy2DAsync(c->d_color[cb] + (size_t)f * fbytes, row, src + (size_t)f * stride, pitch, row,
-                                                pp.H, cudaMemcpyHostToDevice, c->s_copy));
+        int m = n - i;
+        if (m > PRE_CHUNK) m = PRE_CHUNK;
+        if (m > cap - c->pend) m = cap - c->pend;
+        const uint8_t* src = bgr + (size_t)i * stride;
+        uint8_t* dst = c->d_u8[b] + (size_t)c->pend * obytes;
+        if (kind != PTR_DEVICE) {
+            const int cb = c->color_no & 1;
+            c->color_no++;
+            CK(c, cudaStreamWaitEvent(c->s_copy, c->ev_pre[cb], 0));      // kernel that last read d_color[cb]
+            if (kind == PTR_PAGEABLE) {
+                CK(c, cudaEventSynchronize(c->ev_ch2d[cb]));              // DMA that last read h_color[cb]
+                for (int f = 0; f < m; ++f) {
+                    const uint8_t* s0 = src + (size_t)f * stride;
+                    uint8_t* d0 = c->h_color[cb] + (size_t)f * fbytes;
+                    if (pitch == row) memcpy(d0, s0, fbytes);
+                    else for (int y = 0; y < pp.H; ++y) memcpy(d0 + (size_t)y * row, s0 + (size_t)y * pitch, row);
                 }
-                CK(c, cudaEventRecord(c->ev_ch2d[cb], c->s_copy));
-                CK(c, cudaStreamWaitEvent(c->s_comp, c->ev_ch2d[cb], 0));
-                dsrc = c->d_color[cb];
-                dstride = fbytes;
-                dpitch = (int)row;
-                TRY(launch_preprocess(c, dsrc, dstride, dpitch, c->d_u8[b] + (size_t)j * obytes, pp, c->pre_xt, c->pre_yt, m));
-                CK(c, cudaEventRecord(c->ev_pre[cb], c->s_comp));
+                CK(c, cudaMemcpyAsync(c->d_color[cb], c->h_color[cb], (size_t)m * fbytes, cudaMemcpyHostToDevice, c->s_copy));
+            } else if (pitch == row && stride == fbytes) {
+                CK(c, cudaMemcpyAsync(c->d_color[cb], src, (size_t)m * fbytes, cudaMemcpyHostToDevice, c->s_copy));
             } else {
-                TRY(launch_preprocess(c, dsrc, dstride, dpitch, c->d_u8[b] + (size_t)j * obytes, pp, c->pre_xt, c->pre_yt, m));
+                for (int f = 0; f < m; ++f)
+                    CK(c, cudaMemcpy2DAsync(c->d_color[cb] + (size_t)f * fbytes, row, src + (size_t)f * stride, pitch, row,
+                                            pp.H, cudaMemcpyHostToDevice, c->s_copy));
             }
+            CK(c, cudaEventRecord(c->ev_ch2d[cb], c->s_copy));
+            CK(c, cudaStreamWaitEvent(c->s_comp, c->ev_ch2d[cb], 0));
+            TRY(launch_preprocess(c, c->d_color[cb], fbytes, (int)row, dst, pp, c->pre_xt, c->pre_yt, m));
+            CK(c, cudaEventRecord(c->ev_pre[cb], c->s_comp));
+        } else {
+            TRY(launch_preprocess(c, src, stride, (int)pitch, dst, pp, c->pre_xt, c->pre_yt, m));
         }
+        c->pend += m;
+        i += m;
         // the gray frames now sit in the device staging buffer: continue as for device input
-        TRY(process_batch(c, c->d_u8[b], nb, pp.OW, obytes, PTR_DEVICE));
-        i += nb;
+        if (c->pend >= cap) TRY(flush_pending(c));
     }
     return FFB_OK;
 }

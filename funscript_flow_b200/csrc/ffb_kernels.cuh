@@ -1105,15 +1105,17 @@ __global__ void __launch_bounds__(32) k_phase1_finish(FfbP1Args a) {
 // ======================================================================================
 // A5  +-6 centre mean (F:1203-1214)
 // ======================================================================================
-__global__ void __launch_bounds__(128) k_smooth_centers(const int* cx, const int* cy, int n, int j0, int j1,
-                                                        double* centers /* [n][2] */) {
+// cx, cy hold the raw centres of n consecutive pairs of one bracket (the whole bracket, or -- for a shard of
+// it -- the shard plus up to 6 pairs on each side); centre j is written to centers[2 * (j - out_shift)].
+__global__ void __launch_bounds__(128) k_smooth_centers(const int* cx, const int* cy, int n, int j0, int j1, int out_shift,
+                                                        double* centers /* [..][2] */) {
     const int j = j0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= j1) return;
     const int lo = max(0, j - 6), hi = min(n, j + 7);
     long long sx = 0, sy = 0;
     for (int i = lo; i < hi; ++i) { sx += cx[i]; sy += cy[i]; }
-    centers[2 * j] = (double)sx / (double)(hi - lo);
-    centers[2 * j + 1] = (double)sy / (double)(hi - lo);
+    centers[2 * (j - out_shift)] = (double)sx / (double)(hi - lo);
+    centers[2 * (j - out_shift) + 1] = (double)sy / (double)(hi - lo);
 }
 
 // ======================================================================================

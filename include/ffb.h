@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define FFB_VERSION 100
+#define FFB_VERSION 200
 
 #define FFB_OK             0
 #define FFB_E_INVALID     -1   /* bad argument / call out of sequence                     */
@@ -64,6 +64,15 @@ int  ffb_host_free(void* ptr);
  * Farneback parameters are fixed to the reference's call (F:878-879):
  *   pyr_scale 0.5, levels 3, winsize 15, iterations 3, poly_n 5, poly_sigma 1.2, flags 0. */
 int  ffb_configure(ffb_ctx* ctx, int width, int height, int batch_frames, int max_bracket_pairs);
+/* ffb_configure is incremental: a call with the frame size already configured and limits that fit the
+ * allocated capacities changes nothing on the device (no cudaMalloc, no cudaHostAlloc, no synchronisation);
+ * a larger batch or pair limit re-allocates only the buffers that depend on it; invalid arguments leave the
+ * existing configuration untouched.  Results never depend on the capacities.
+ * ffb_get_geometry returns the frame size and limits of the last successful ffb_configure (0s before it);
+ * ffb_alloc_counts the cudaMalloc / cudaHostAlloc calls this context has made so far (a runner that
+ * configures once per video must see them stand still after the first bracket). */
+int  ffb_get_geometry(const ffb_ctx* ctx, int* width, int* height, int* batch_frames, int* max_bracket_pairs);
+int  ffb_alloc_counts(const ffb_ctx* ctx, int64_t* device_allocs, int64_t* host_allocs);
 
 /* ---- streaming bracket API (replaces the bracket loop body F:1188-1242) ------------------
  * A bracket is a run of consecutive sampled frames; pairs never span brackets (F:1150-1153,
@@ -88,6 +97,27 @@ int  ffb_bracket_begin(ffb_ctx* ctx, int pov_mode, double cut_threshold);
 int  ffb_bracket_push(ffb_ctx* ctx, const uint8_t* frames, int n_frames, size_t pitch, size_t frame_stride);
 int  ffb_bracket_finish(ffb_ctx* ctx, int* n_pairs, double* scalar, uint8_t* cut, int32_t* cx, int32_t* cy,
                         float* val, float* mean_mag, double* centers);
+/* ---- frame-range shards of one bracket (reference semantics F:1188, F:1203-1214) ----
+ * A GPU that owns pairs [a, b) of a bracket pushes frames a .. b (one frame of overlap with the next
+ * shard) and needs, for the +-6 centre window, the raw centres of pairs [a-6, b+6) clipped to the bracket;
+ * those of its neighbours come from the GPUs that computed them.  The bracket is therefore run in two phases:
+ *
+ *   ffb_bracket_begin_shard(ctx, pov_mode, cut_threshold, shard_pairs)   final flows of all shard_pairs stay resident
+ *   ffb_bracket_push / ffb_bracket_push_bgr ...                          flow, centre, cut test per pair (A1-A4)
+ *   ffb_bracket_phase1_finish(ctx, &n, cx, cy, val, mean_mag, cut)       raw per-pair results of the shard
+ *       ... the host exchanges (cx, cy) with the neighbouring shards (an all_gather of int32[2] per pair) ...
+ *   ffb_bracket_radial(ctx, cx_ext, cy_ext, n_ext, first, scalar, centers)
+ *
+ * cx_ext / cy_ext: raw centres of the n_ext consecutive pairs [a - first, a - first + n_ext) of the bracket,
+ * 0 <= first <= 6 and at most 6 pairs beyond the shard's last one, already clipped to the bracket (so the
+ * window truncation at bracket ends falls out of the array bounds, exactly as F:1203-1214 truncates).
+ * Outputs: scalar[j], centers[2j..2j+1] for the shard's pairs; this call ends the bracket.  A whole bracket
+ * pushed as one shard (first = 0, n_ext = n) returns what ffb_bracket_finish returns, bit for bit. */
+int  ffb_bracket_begin_shard(ffb_ctx* ctx, int pov_mode, double cut_threshold, int shard_pairs);
+int  ffb_bracket_phase1_finish(ffb_ctx* ctx, int* n_pairs, int32_t* cx, int32_t* cy, float* val, float* mean_mag,
+                               uint8_t* cut);
+int  ffb_bracket_radial(ffb_ctx* ctx, const int32_t* cx_ext, const int32_t* cy_ext, int n_ext, int first,
+                        double* scalar, double* centers);
 /* Drop the open bracket without results (after an error, or on user cancel: F:1147-1149 "User bailed"):
  * waits for the device work already queued, then leaves the context ready for ffb_bracket_begin /
  * ffb_configure.  A no-op outside a bracket. */

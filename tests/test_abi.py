@@ -41,7 +41,7 @@ def test_library_is_sm100a(lib_path):
 
 def test_version_and_level_plan(lib_path):
     lib = _native.load(lib_path)
-    assert lib.ffb_version() == 100
+    assert lib.ffb_version() == 200
     plan = _native.level_plan(1920, 1080, lib_path)
     assert [(p["w"], p["h"], p["ksize"]) for p in plan] == [(240, 135, 19), (480, 270, 9), (960, 540, 3), (1920, 1080, 3)]
     assert [(p["w"], p["h"]) for p in _native.level_plan(517, 389, lib_path)] == [(65, 49), (129, 97), (258, 194), (517, 389)]

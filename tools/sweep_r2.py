@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
-KNOBS = ("FFB_ITER_CFG", "FFB_ITER_CFG_COARSE", "FFB_ITER_OPT", "FFB_ITER_SWMAX", "FFB_ITER_SH", "FFB_ITER_MINSEG",
+KNOBS = ("FFB_ITER_CFG", "FFB_ITER_CFG_COARSE", "FFB_ITER_CFG_K0", "FFB_ITER_CFG_K1", "FFB_ITER_CFG_K2", "FFB_ITER_CFG_K3", "FFB_ITER_OPT", "FFB_ITER_SWMAX", "FFB_ITER_SH", "FFB_ITER_MINSEG",
          "FFB_FLOW_STREAMS", "FFB_POLY", "FFB_DIV", "FFB_PYR")
 
 
@@ -40,13 +40,17 @@ def main():
         name, _, envs = spec.partition(":")
         for k in KNOBS:
             os.environ.pop(k, None)
+        batch = args.batch
         for kv in filter(None, envs.split(",")):
             k, v = kv.split("=")
-            os.environ[k] = v
+            if k == "BATCH":          # pseudo-knob: frames per GPU batch of this configuration
+                batch = int(v)
+            else:
+                os.environ[k] = v
         out = {"name": name, "env": envs}
         try:
             ctx = _native.FlowContext(0)
-            ctx.configure(W, H, args.batch, P)
+            ctx.configure(W, H, batch, P)
 
             def step():
                 ctx.bracket_begin(False, 7.0)
