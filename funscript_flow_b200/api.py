@@ -129,6 +129,52 @@ def process_bracket(frames, params: Optional[Dict] = None, *, ctx: Optional[_nat
     return res
 
 
+def shard_bounds(n_pairs: int, parts: int):
+    """Contiguous, balanced pair ranges [a, b) of a bracket of n_pairs pairs for `parts` GPUs: shard r
+    needs frames a .. b (one frame of overlap with shard r+1).  Ranges may be empty when parts > n_pairs."""
+    return [(n_pairs * r // parts, n_pairs * (r + 1) // parts) for r in range(parts)]
+
+
+def shard_phase1(ctx: _native.FlowContext, frames, a: int, b: int, params: Optional[Dict] = None,
+                 batch_frames: int = DEFAULT_BATCH_FRAMES) -> Dict:
+    """Phase 1 of pairs [a, b) of the bracket `frames` on `ctx` (flows, raw centres, cut test; F:1188-1199).
+    The shard's final flows stay resident in `ctx` until shard_phase2."""
+    params = params or {}
+    arr = _as_frames(frames[a:b + 1])
+    n, h, w = arr.shape
+    ctx.configure(w, h, max(1, min(batch_frames, n)), max(n - 1, 1))
+    ctx.bracket_begin_shard(n - 1, bool(params.get("pov_mode", False)), float(params.get("cut_threshold", DEFAULT_CUT_THRESHOLD)))
+    try:
+        ctx.bracket_push(arr)
+        return ctx.bracket_phase1_finish()
+    except BaseException:
+        ctx.bracket_abort()
+        raise
+
+
+def shard_phase2(ctx: _native.FlowContext, cx_all: np.ndarray, cy_all: np.ndarray, a: int, b: int):
+    """Phase 2 of pairs [a, b): cx_all / cy_all are the raw centres of ALL pairs of the bracket (gathered from the
+    shards); the +-6 window (F:1201-1214) reads [a-6, b+6) clipped to the bracket.  Returns (scalar, centers)."""
+    lo, hi = max(0, a - 6), min(len(cx_all), b + 6)
+    return ctx.bracket_radial(cx_all[lo:hi], cy_all[lo:hi], a - lo, b - a)
+
+
+def process_bracket_on_contexts(frames, params: Optional[Dict], ctxs: Sequence[_native.FlowContext],
+                                batch_frames: int = DEFAULT_BATCH_FRAMES) -> Dict:
+    """One bracket cut into len(ctxs) frame-range shards, shard r on ctxs[r] (several GPUs driven by one process, or
+    several contexts of one GPU).  Same dict as process_bracket, bit for bit."""
+    arr = _as_frames(frames)
+    n_pairs = len(arr) - 1
+    bounds = shard_bounds(n_pairs, len(ctxs))
+    p1 = [shard_phase1(c, arr, a, b, params, batch_frames) if b > a else None for c, (a, b) in zip(ctxs, bounds)]
+    cat = {k: np.concatenate([p[k] for p in p1 if p is not None]) for k in ("cx", "cy", "val", "mean_mag", "cut")}
+    parts = [shard_phase2(c, cat["cx"], cat["cy"], a, b) for c, (a, b) in zip(ctxs, bounds) if b > a]
+    cat["scalar"] = np.concatenate([p[0] for p in parts])
+    cat["centers"] = np.concatenate([p[1] for p in parts])
+    cat["n_pairs"] = n_pairs
+    return cat
+
+
 def precompute_flow_info(p0: np.ndarray, p1: np.ndarray, config: Dict) -> Dict:
     """F:843-907.  `config["backend"]` is ignored (there is one backend); `pov_mode` and the
     hidden `cut_threshold` key are honoured like the CPU branch (F:876-894)."""
@@ -139,7 +185,7 @@ def precompute_flow_info(p0: np.ndarray, p1: np.ndarray, config: Dict) -> Dict:
         raise ValueError("p0 and p1 must be equal-sized 2-D uint8 arrays")
     h, w = p0.shape
     pov = bool(config.get("pov_mode"))
-    ctx.configure(w, h, 2, 64)
+    ctx.configure(w, h, 2, 1)       # incremental: a context already configured for this frame size is left alone
     ctx.bracket_begin(pov, float(config.get("cut_threshold", DEFAULT_CUT_THRESHOLD)))
     try:
         ctx.bracket_push(p0)

@@ -61,16 +61,24 @@ def process_frames(frames: Sequence[np.ndarray], fps: float, params: Dict, frame
     return actions
 
 
-def iter_sampled_bgr(video_path: str, indices: Sequence[int]):
-    """Decode the sampled frames (BGR, as cv2.VideoCapture returns them); undecodable frames are black
-    (F:274-280).  Sequential read + grab instead of the reference's per-frame seek."""
+def _container_shape(cap):
+    """(H, W, 3) of the frames a cv2.VideoCapture delivers, None when the container does not say."""
+    import cv2
+    w, h = int(cap.get(cv2.CAP_PROP_FRAME_WIDTH)), int(cap.get(cv2.CAP_PROP_FRAME_HEIGHT))
+    return (h, w, 3) if w > 0 and h > 0 else None
+
+
+def iter_sampled_bgr(video_path: str, indices: Sequence[int], shape_hint=None):
+    """Decode the sampled frames (BGR, as cv2.VideoCapture returns them); undecodable frames are black at the
+    container's frame size (F:239-245, F:274-280: a file that over-reports its frame count still yields a script).
+    Sequential read + grab instead of the reference's per-frame seek."""
     import cv2
     cap = cv2.VideoCapture(video_path)
     if not cap.isOpened():
         raise IOError(f"cannot open {video_path}")
     want = set(int(i) for i in indices)
     last = max(want) if want else -1
-    shape = None
+    shape = shape_hint or _container_shape(cap)
     pos = 0
     while pos <= last:
         if pos in want:
@@ -78,7 +86,9 @@ def iter_sampled_bgr(video_path: str, indices: Sequence[int]):
             if ok:
                 shape = frame.shape
             else:
-                frame = np.zeros(shape or (256, 256, 3), np.uint8)
+                if shape is None:
+                    raise IOError(f"{video_path}: no frame could be decoded and the container reports no frame size")
+                frame = np.zeros(shape, np.uint8)
             yield frame
         else:
             cap.grab()
@@ -88,7 +98,8 @@ def iter_sampled_bgr(video_path: str, indices: Sequence[int]):
 
 def _decode_span(video_path: str, wanted: Sequence[int], shape_hint):
     """Frames `wanted` (increasing indices) from their own cv2.VideoCapture: seek to the first, then read / grab
-    forward.  Returns (frames, seek_ok); seek_ok is False when the container did not land on the requested frame."""
+    forward.  Returns (frames, seek_ok); seek_ok is False when the container did not land on the requested frame.
+    Frames that cannot be read are black at the container's frame size (`shape_hint`, else what the handle reports)."""
     import cv2
     cap = cv2.VideoCapture(video_path)
     out = []
@@ -99,14 +110,16 @@ def _decode_span(video_path: str, wanted: Sequence[int], shape_hint):
             cap.set(cv2.CAP_PROP_POS_FRAMES, first)
             ok_seek = int(round(cap.get(cv2.CAP_PROP_POS_FRAMES))) == first
         want = set(int(i) for i in wanted)
-        pos, last, shape = first, int(wanted[-1]), shape_hint
+        pos, last, shape = first, int(wanted[-1]), shape_hint or _container_shape(cap)
         while pos <= last:
             if pos in want:
                 ok, frame = cap.read()
                 if ok:
                     shape = frame.shape
                 else:
-                    frame = np.zeros(shape or (256, 256, 3), np.uint8)       # F:274-280
+                    if shape is None:
+                        raise IOError(f"{video_path}: no frame could be decoded and the container reports no frame size")
+                    frame = np.zeros(shape, np.uint8)       # F:274-280
                 out.append(frame)
             else:
                 cap.grab()
@@ -116,7 +129,7 @@ def _decode_span(video_path: str, wanted: Sequence[int], shape_hint):
     return out, ok_seek
 
 
-def iter_sampled_bgr_parallel(video_path: str, indices: Sequence[int], workers: int = 4, span: int = 64):
+def iter_sampled_bgr_parallel(video_path: str, indices: Sequence[int], workers: int = 4, span: int = 64, shape_hint=None):
     """iter_sampled_bgr with the decode spread over `workers` threads (the reference decodes on up to 4 handles,
     F:103-291): the sampled indices are cut into spans of `span` frames, each span is decoded on its own
     VideoCapture (cv2 releases the GIL while decoding) and the spans are handed out in order with a bounded
@@ -125,7 +138,7 @@ def iter_sampled_bgr_parallel(video_path: str, indices: Sequence[int], workers: 
     from concurrent.futures import ThreadPoolExecutor
     idx = [int(i) for i in indices]
     if workers <= 1 or len(idx) <= span:
-        yield from iter_sampled_bgr(video_path, idx)
+        yield from iter_sampled_bgr(video_path, idx, shape_hint)
         return
     spans = [idx[a:a + span] for a in range(0, len(idx), span)]
     with ThreadPoolExecutor(max_workers=workers) as pool:
@@ -135,7 +148,7 @@ def iter_sampled_bgr_parallel(video_path: str, indices: Sequence[int], workers: 
         def fill():
             nonlocal nxt
             while nxt < len(spans) and len(pending) < workers + 1:
-                pending[nxt] = pool.submit(_decode_span, video_path, spans[nxt], None)
+                pending[nxt] = pool.submit(_decode_span, video_path, spans[nxt], shape_hint)
                 nxt += 1
         fill()
         for k in range(len(spans)):
@@ -144,7 +157,7 @@ def iter_sampled_bgr_parallel(video_path: str, indices: Sequence[int], workers: 
                 for fut in pending.values():
                     fut.cancel()
                 rest = [i for sp in spans[k:] for i in sp]
-                yield from iter_sampled_bgr(video_path, rest)
+                yield from iter_sampled_bgr(video_path, rest, shape_hint)
                 return
             fill()
             yield from frames
@@ -242,7 +255,13 @@ def process_video_series(video_path: str, params: Dict, ctx=None, progress_callb
     cuts: List[bool] = []
     stamps: List[int] = []
     # `threads` is the reference's pool size (F:2654); here it bounds the decode threads (the GPU needs none)
-    frames = iter_sampled_bgr_parallel(video_path, indices, workers=max(1, min(4, int(params.get("threads", 4)))))
+    frames = iter_sampled_bgr_parallel(video_path, indices, workers=max(1, min(4, int(params.get("threads", 4)))),
+                                       shape_hint=(src_h, src_w, 3))
+    # one configuration per video: batch size fixed, pair limit of the longest bracket (ffb_configure is incremental,
+    # so the shorter last bracket re-allocates nothing)
+    max_pairs = min(bracket, len(indices)) - 1
+    for c in ctxs:
+        c.configure(out_w, out_h, max(1, min(batch, max_pairs + 1)), max(1, max_pairs))
     done = 0
     for a in range(0, len(indices), bracket):
         b = min(a + bracket, len(indices))
@@ -254,7 +273,6 @@ def process_video_series(video_path: str, params: Dict, ctx=None, progress_callb
                 next(frames, None)
             continue
         for c in ctxs:
-            c.configure(out_w, out_h, max(1, min(batch, nfr)), nfr - 1)
             c.bracket_begin(bool(params.get("pov_mode", False)), cut_threshold)
         try:
             got = 0

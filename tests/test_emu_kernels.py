@@ -325,3 +325,110 @@ def test_process_video_log_lines_follow_the_reference(emu_ctx, tmp_path):
     runner.process_video(path, dict(prm, overwrite=False), ours.append)
     ref.process_video(path, dict(prm, overwrite=False), theirs.append)
     assert ours == theirs
+
+
+def test_configure_is_incremental(emu_lib):
+    """ffb_configure re-allocates only what a request outgrows: same or smaller limits touch nothing (no cudaMalloc,
+    no cudaHostAlloc -- counted by the library), a refused call leaves the configuration usable, and results do not
+    depend on the capacities a context happens to hold."""
+    from funscript_flow_b200 import _native
+    ctx = _native.FlowContext(0, emu_lib)
+    assert ctx.geometry is None
+    clip = make_clip(96, 64, 9, seed=12)
+    ref = api.process_bracket(clip, {}, ctx=ctx, batch_frames=4)
+    base = ctx.alloc_counts()
+    assert base[0] > 0 and base[1] > 0 and ctx.geometry == (96, 64, 4, 8)
+    for _ in range(3):                                        # bracket after bracket of one video: nothing is allocated
+        again = api.process_bracket(clip, {}, ctx=ctx, batch_frames=4)
+    assert ctx.alloc_counts() == base and np.array_equal(again["scalar"], ref["scalar"])
+    short = api.process_bracket(clip[:5], {}, ctx=ctx, batch_frames=4)        # a shorter last bracket
+    assert ctx.alloc_counts() == base and ctx.geometry == (96, 64, 4, 4)
+    assert np.array_equal(short["cx"], ref["cx"][:4])
+    # the per-pair drop-in functions reuse the configuration of the same frame size
+    api.set_context(ctx)
+    info = api.precompute_flow_info(clip[0], clip[1], {})
+    api.radial_motion_weighted(info["flow"], (40.0, 30.0), False)
+    api.max_divergence(info["flow"])
+    assert ctx.alloc_counts() == base
+    # a bad request is refused before anything is freed
+    with pytest.raises(_native.FFBError) as ei:
+        ctx.configure(8, 8, 4, 8)
+    assert ei.value.code == -1 and ctx.alloc_counts() == base and ctx.geometry[:2] == (96, 64)
+    assert np.array_equal(api.process_bracket(clip, {}, ctx=ctx, batch_frames=4)["scalar"], ref["scalar"])
+    # growing one limit re-allocates that group only: more pairs -> the per-pair arrays, not the per-batch buffers
+    ctx.configure(96, 64, 4, 100)
+    grown = ctx.alloc_counts()
+    assert 0 < grown[0] - base[0] < base[0] // 2 and grown[1] - base[1] == 1
+    big = api.process_bracket(clip, {}, ctx=ctx, batch_frames=8)              # larger batch: per-batch buffers grow
+    assert ctx.alloc_counts()[0] > grown[0] and np.array_equal(big["scalar"], ref["scalar"])
+    ctx.close()
+
+
+def test_shard_api_sequence_and_errors(emu_lib):
+    """Two-phase shard brackets through the C ABI: call order is enforced, the external centre frame is validated, a whole
+    bracket as a single shard equals ffb_bracket_finish, and an aborted shard leaves the context usable."""
+    from funscript_flow_b200 import _native
+    ctx = _native.FlowContext(0, emu_lib)
+    clip = make_clip(96, 64, 11, seed=4, period=6.0, amplitude=0.3)
+    ref = api.process_bracket(clip, {}, ctx=ctx, batch_frames=4)
+    ctx.configure(96, 64, 4, 10)
+    with pytest.raises(_native.FFBError):
+        ctx.bracket_phase1_finish()                                      # no bracket
+    ctx.bracket_begin(False, 7.0)
+    with pytest.raises(_native.FFBError):
+        ctx.bracket_phase1_finish()                                      # not a shard bracket
+    with pytest.raises(_native.FFBError):
+        ctx.bracket_begin_shard(4)                                       # a bracket is open
+    ctx.bracket_abort()
+    ctx.bracket_begin_shard(10)
+    ctx.bracket_push(clip)
+    with pytest.raises(_native.FFBError):
+        ctx.bracket_finish()                                             # shard brackets end with bracket_radial
+    with pytest.raises(_native.FFBError):
+        ctx.bracket_radial(ref["cx"], ref["cy"], 0, 10)                  # phase 1 has not been read
+    p1 = ctx.bracket_phase1_finish()
+    assert p1["n_pairs"] == 10 and np.array_equal(p1["cx"], ref["cx"]) and np.array_equal(p1["cut"], ref["cut"])
+    with pytest.raises(_native.FFBError):
+        ctx.bracket_push(clip[:2])                                       # no frames after phase 1
+    for bad in ((p1["cx"][:9], p1["cy"][:9], 0), (p1["cx"], p1["cy"], 7), (np.zeros(17, np.int32), np.zeros(17, np.int32), 0)):
+        with pytest.raises(_native.FFBError):
+            ctx.bracket_radial(bad[0], bad[1], bad[2], 10)
+    scalar, centers = ctx.bracket_radial(p1["cx"], p1["cy"], 0, 10)
+    assert np.array_equal(scalar, ref["scalar"]) and np.array_equal(centers, ref["centers"])
+    # more pairs than announced are refused; abort recovers
+    ctx.bracket_begin_shard(3)
+    with pytest.raises(_native.FFBError):
+        ctx.bracket_push(np.concatenate([clip] * 3))
+    ctx.bracket_abort()
+    assert np.array_equal(api.process_bracket(clip, {}, ctx=ctx, batch_frames=4)["scalar"], ref["scalar"])
+    ctx.close()
+
+
+def test_colour_pushes_gather_into_full_batches(emu_lib):
+    """ffb_bracket_push_bgr accumulates pre-processed frames until a GPU batch is full, however the caller cuts its
+    pushes (64-frame chunks never reached the 128 / 512-frame batches of small frames): pushing one
+    frame at a time launches as many kernels as one push of the whole bracket, and gives the same numbers."""
+    import cv2
+    from funscript_flow_b200 import _native
+    ctx = _native.FlowContext(0, emu_lib)
+    gray = make_clip(96, 64, 13, seed=9)
+    bgr = np.stack([cv2.cvtColor(f, cv2.COLOR_GRAY2BGR) for f in gray])
+    ctx.preprocess_configure_window(96, 64, (96, 64), (0, 0, 96, 64))
+
+    def run(step):
+        ctx.configure(96, 64, 8, 12)
+        ctx.bracket_begin(False, 7.0)
+        l0 = ctx.launch_count
+        for a in range(0, len(bgr), step):
+            ctx.bracket_push_bgr(bgr[a:a + step])
+        r = ctx.bracket_finish()
+        return r, ctx.launch_count - l0
+    whole, n_whole = run(len(bgr))
+    single, n_single = run(1)
+    threes, n_threes = run(3)
+    assert np.array_equal(whole["scalar"], single["scalar"]) and np.array_equal(whole["scalar"], threes["scalar"])
+    # only the per-chunk pre-processing launches differ (chunks of <= 8 colour frames): the flow batches are the same
+    assert n_single - n_whole == len(bgr) - 3 and n_threes - n_whole <= 3
+    ref = api.process_bracket(gray, {}, ctx=ctx, batch_frames=8)
+    assert np.array_equal(ref["scalar"], whole["scalar"])
+    ctx.close()

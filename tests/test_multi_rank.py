@@ -1,5 +1,6 @@
-"""CPU suite, part 4: the N>1 host logic with world_size 2 over gloo (no GPU): bracket sharding and
-the gather of per-pair scalars give exactly the single-process result.  The compute engine in this
+"""CPU suite, part 4: the N>1 host logic with world_size 2 over gloo (no GPU): frame-range sharding inside a
+bracket (one frame of overlap, all-gather of the raw centres), bracket sharding and the gather of per-pair
+scalars give exactly the single-process result.  The compute engine in this
 test is the g++ emulation of the kernels (test infrastructure)."""
 import json
 import os
@@ -22,10 +23,13 @@ api.set_context(ctx)
 rank, ws = distributed.init("gloo")
 clip = make_clip(96, 64, 17, seed=8, period=7.0, amplitude=0.3)
 prm = {{"batch_size": 6, "detrend_window": 2.0, "norm_window": 3.0, "keyframe_reduction": True}}
-acts, series = distributed.process_frames_sharded(clip, 30.0, prm, ctx=ctx)
+acts, series = distributed.process_frames_sharded(clip, 30.0, prm, ctx=ctx)                     # frame ranges inside every bracket
+acts_b, series_b = distributed.process_frames_sharded(clip, 30.0, prm, ctx=ctx, mode="brackets")  # whole brackets round-robin
+one = distributed.process_bracket_sharded(clip, {{}}, ctx=ctx, batch_frames=4)                    # the clip as ONE bracket over all ranks
 if rank == 0:
     json.dump({{"actions": acts, "values": series["values"].tolist(), "idx": series["frame_indices"].tolist(),
-               "ws": ws}}, open({out!r}, "w"))
+               "actions_b": acts_b, "values_b": series_b["values"].tolist(),
+               "one": {{k: np.asarray(v).tolist() for k, v in one.items()}}, "ws": ws}}, open({out!r}, "w"))
 import torch.distributed as dist
 if dist.is_initialized():
     dist.barrier(); dist.destroy_process_group()
@@ -53,6 +57,12 @@ def test_bracket_sharding_world2_equals_single(emu_lib, tmp_path):
     assert multi["idx"] == single["idx"]
     assert multi["values"] == single["values"]          # bit-for-bit
     assert multi["actions"] == single["actions"]
+    # both sharding modes agree with each other and with the single process
+    assert multi["values_b"] == single["values"] and single["values_b"] == single["values"]
+    assert multi["actions_b"] == single["actions"]
+    # one 16-pair bracket cut into two frame ranges (8 pairs each, one frame of overlap, raw centres all-gathered
+    # between the phases): every per-pair output equals the single-GPU bracket, the +-6 window across the seam included
+    assert multi["one"] == single["one"] and single["one"]["n_pairs"] == 16
 
 
 def test_video_sharding():
@@ -155,3 +165,27 @@ def test_parallel_decode_returns_the_same_frames(tmp_path):
     finally:
         runner._decode_span = real
     assert all(np.array_equal(a, b) for a, b in zip(runner.iter_sampled_bgr(path, list(range(90))), par)) and len(par) == 90
+
+
+def test_frames_past_the_end_are_black_at_the_container_size(tmp_path):
+    """A container that over-reports its frame count by a span or more (truncated file, broken index): the reference
+    fills the missing frames with black at the real frame size and still writes a script (F:239-245, F:274-280).
+    Round-1 ADVICE: spans whose reads all failed came back as 256x256 frames and np.stack raised."""
+    cv2 = pytest.importorskip("cv2")
+    from funscript_flow_b200 import runner
+    from funscript_flow_b200.synth import make_clip
+    clip = make_clip(320, 240, 100, seed=6, period=9.0, amplitude=0.2)
+    path = str(tmp_path / "short.avi")
+    vw = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), 30.0, (320, 240), True)
+    if not vw.isOpened():
+        pytest.skip("MJPG writer unavailable")
+    for f in clip:
+        vw.write(cv2.cvtColor(f, cv2.COLOR_GRAY2BGR))
+    vw.release()
+    want = list(range(200))                                   # twice what the file holds
+    for frames in (list(runner.iter_sampled_bgr(path, want)),
+                   list(runner.iter_sampled_bgr_parallel(path, want, workers=4, span=16)),
+                   list(runner.iter_sampled_bgr_parallel(path, want, workers=4, span=16, shape_hint=(240, 320, 3)))):
+        assert len(frames) == 200 and {f.shape for f in frames} == {(240, 320, 3)}
+        assert np.stack(frames).shape == (200, 240, 320, 3)
+        assert frames[50].any() and not frames[150].any()     # decoded, then black
