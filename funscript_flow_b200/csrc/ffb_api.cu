@@ -418,16 +418,25 @@ int launch_polyexp(ffb_ctx* c, const float* src, size_t src_stride, int sp, int 
     FfbPolyArgs a;
     a.src = src; a.src_frame_stride = src_stride; a.sp = sp; a.w = w; a.h = h;
     a.dst = dst; a.plane = plane; a.rp = rp; a.c = c->poly;
+    a.aligned2 = (sp % 2 == 0) && (src_stride % 2 == 0) && ((uintptr_t)src % 8 == 0);
     // the kernel stores two pixels (32 bytes) of the float4 image per instruction
     if (rp % 4 != 0 || ((uintptr_t)dst.base | (uintptr_t)dst.stride) % 32 != 0)
         return fail(c, FFB_E_INVALID, "expansion output is not 32-byte aligned (pitch %d, stride %zu)", rp, dst.stride);
     if (!c->attr_poly) {
         CK(c, cudaFuncSetAttribute(k_polyexp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POLY_SMEM));
+        CK(c, cudaFuncSetAttribute(k_polyexp2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POLY2_SMEM));
         c->attr_poly = true;
     }
-    dim3 grid((w + POLY_OW - 1) / POLY_OW, (h + POLY_ROWS - 1) / POLY_ROWS, nframes);
+    // FFB_POLY=0: the scalar kernel (kept for A/B runs); default: two rows at a time with packed fp32 arithmetic
+    const bool packed = !(getenv("FFB_POLY") && atoi(getenv("FFB_POLY")) == 0);
     prof_begin(c, FFB_K_POLYEXP, (double)nframes * 24.0 * w * h);
-    FFB_LAUNCH(k_polyexp, grid, dim3(256), POLY_SMEM, c->s_comp, a);
+    if (packed) {
+        dim3 grid((w + POLY_OW - 1) / POLY_OW, (h + POLY2_ROWS - 1) / POLY2_ROWS, nframes);
+        FFB_LAUNCH(k_polyexp2, grid, dim3(256), POLY2_SMEM, c->s_comp, a);
+    } else {
+        dim3 grid((w + POLY_OW - 1) / POLY_OW, (h + POLY_ROWS - 1) / POLY_ROWS, nframes);
+        FFB_LAUNCH(k_polyexp, grid, dim3(256), POLY_SMEM, c->s_comp, a);
+    }
     prof_end(c);
     CKL(c);
     return FFB_OK;
@@ -449,30 +458,27 @@ int launch_upsample(ffb_ctx* c, const float2* src, size_t src_stride, int sp, in
 }
 
 // Tunables of the fused iteration kernel.  The defaults are compiled in; the environment overrides exist for
-// tuning runs and for the tests that force a variant onto small frames:
-//   FFB_ITER_CFG=NTxUxHO   threads per CTA (= matrix columns per strip) x rows per step x outputs per horizontal task
-//   FFB_ITER_CFG_COARSE    same, for the levels k >= 2 only
-//   FFB_ITER_OPT           bit 0: non-allocating loads of R0 / flow-in, bit 1: bulk L2 prefetch (128x2x4 only)
+// tuning runs and for the tests that force a variant onto small frames (parsed per launch):
+//   FFB_ITER_CFG=NTxUxHO   threads per CTA (= matrix columns per strip) x rows per step x outputs per horizontal task;
+//                          compiled in: 256x4x8, 128x2x4, 160x2x4 (the round-2 sweeps measured and dropped 96 / 192 /
+//                          512-thread strips, 8-output tasks on 2-row steps, 4-output tasks on 4-row steps, non-allocating
+//                          loads, bulk L2 prefetch and early issue of the second row pair: profiles/r2_sweep_flow_iter.txt)
+//   FFB_ITER_CFG_K<k>      the same for pyramid level k only
 //   FFB_ITER_SH / FFB_ITER_MINSEG   rows per march segment (upper bound) / minimum segments per level
 //   FFB_ITER_SWMAX=0       equal-width strips (round 1) instead of full-width strips plus a narrow last one
-struct IterCfg { int nt, u, ho, sh, opt, swmax; int cnt, cu, cho; };
-IterCfg iter_cfg() {      // parsed per launch (a few getenv calls): tuning runs switch variants inside one process
-    IterCfg c{0, 2, 4, 270, 0, 1, 0, 2, 4};
+struct IterCfg { int nt, u, ho, sh, swmax; };
+IterCfg iter_cfg() {
+    IterCfg c{0, 2, 4, 270, 1};
     if (const char* e = getenv("FFB_ITER_CFG")) {
         int nt = 0, u = 0, ho = 0;
         if (sscanf(e, "%dx%dx%d", &nt, &u, &ho) == 3) { c.nt = nt; c.u = u; c.ho = ho; }
     }
-    if (const char* e = getenv("FFB_ITER_CFG_COARSE")) {
-        int nt = 0, u = 0, ho = 0;
-        if (sscanf(e, "%dx%dx%d", &nt, &u, &ho) == 3) { c.cnt = nt; c.cu = u; c.cho = ho; }
-    }
     if (const char* e = getenv("FFB_ITER_SH")) { const int v = atoi(e); if (v >= 16) c.sh = v; }
-    if (const char* e = getenv("FFB_ITER_OPT")) c.opt = atoi(e) & 3;
     if (const char* e = getenv("FFB_ITER_SWMAX")) c.swmax = atoi(e) != 0;
     return c;
 }
 
-template <int NT, int U, int MINB, int HO = 4, int OPT = 0>
+template <int NT, int U, int MINB, int HO>
 int launch_flow_iter_t(ffb_ctx* c, FfbIterArgs a, int npairs, int sh_target, double bytes) {
     const int w = a.w, h = a.h;
     const int sw_max = (NT - 2 * FFB_WIN_R) / HO * HO;
@@ -490,10 +496,10 @@ int launch_flow_iter_t(ffb_ctx* c, FfbIterArgs a, int npairs, int sh_target, dou
     // at most sh_target rows per segment, at least min_seg segments per level (coarse levels would
     // otherwise be a handful of long, latency-bound marches), never under 32 rows
     const int min_seg_env = getenv("FFB_ITER_MINSEG") ? atoi(getenv("FFB_ITER_MINSEG")) : 0;
-    // frames of 1280x720 and more: at least 3 segments on every level (parallelism for their 64-pair batches; 3 beats 4
-    // by 0.5 % and 2 loses 0.5 % at 1080p); smaller frames come in batches of hundreds, and every segment pays 14 halo
-    // rows: 2 (+7 % at 256x256, +3.5 % at 640x360) -- profiles/r1_sweep_segments.txt.  The rule looks at the frame
-    // the context is configured for, never at the batch.
+    // frames of 1280x720 and more: at least 3 segments on every level (parallelism for their 64-pair batches; 2 .. 4
+    // measure the same at 1080p, 5 and more lose); smaller frames come in batches of hundreds, and every segment pays
+    // 14 halo rows: 2 (+7 % at 256x256, +3.5 % at 640x360) -- profiles/r1_sweep_segments.txt, r2_sweep_flow_iter.txt.
+    // The rule looks at the frame the context is configured for, never at the batch.
     const long long frame_px = c->seg_frame_px > 0 ? c->seg_frame_px : (long long)w * h;      // stage hooks: the level itself
     const int min_seg = min_seg_env > 0 ? min_seg_env : (frame_px >= 1280LL * 720 ? 3 : 2);
     int nseg = (h + sh_target - 1) / sh_target;
@@ -502,7 +508,7 @@ int launch_flow_iter_t(ffb_ctx* c, FfbIterArgs a, int npairs, int sh_target, dou
     if (nseg < 1) nseg = 1;
     a.SH = ffb_round_up((h + nseg - 1) / nseg, U);     // even: see the fused up-sampling in k_flow_iter
     const int gy = (h + a.SH - 1) / a.SH;
-    auto kfn = a.up_src ? k_flow_iter<NT, U, MINB, true, HO, OPT> : k_flow_iter<NT, U, MINB, false, HO, OPT>;
+    auto kfn = a.up_src ? k_flow_iter<NT, U, MINB, true, HO> : k_flow_iter<NT, U, MINB, false, HO>;
     const size_t smem = ffb_flow_iter_smem<NT, U, HO>();
     if (!c->attr_iter.count((const void*)kfn)) {
         CK(c, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -541,7 +547,6 @@ int launch_flow_iter(ffb_ctx* c, FfbRing R, size_t plane, int rp, int w, int h, 
         return fail(c, FFB_E_INVALID, "flow output is not 32-byte aligned (pitch %d, stride %zu)", fop, fout.stride);
     const IterCfg k = iter_cfg();
     int nt = k.nt, u = k.u, ho = k.ho;
-    if (k.cnt > 0 && c->cur_level >= 2) { nt = k.cnt; u = k.cu; ho = k.cho; }
     if (c->cur_level >= 0 && c->cur_level < FFB_MAX_LEVELS) {      // FFB_ITER_CFG_K<k>: one level only
         char name[24];
         snprintf(name, sizeof(name), "FFB_ITER_CFG_K%d", c->cur_level);
@@ -555,7 +560,7 @@ int launch_flow_iter(ffb_ctx* c, FfbRing R, size_t plane, int rp, int w, int h, 
         // is configured for (never on the batch):
         //   1280x720 and larger   256 threads, 4 rows per step, 8 outputs per horizontal task: 242-column strips carry
         //                         5.5 % halo columns instead of 10.9 %, and the 120 horizontal tasks of a step fill 4 of
-        //                         the 8 warps (1080p: +8.4 % over 128x2x4, 4K: +7 %)
+        //                         the 8 warps (1080p: +8.4 % over 128x2x4, 4K: +7 %, 720p: +1 %)
         //   up to 320 columns     160 threads x 2 rows x 4 outputs (the reference's 256x256 product mode: 2 strips)
         //   in between            128 threads x 2 rows x 4 outputs (640x360: +8 % over 160x2x4)
         const long long frame_px = c->seg_frame_px > 0 ? c->seg_frame_px : (long long)w * h;
@@ -565,29 +570,12 @@ int launch_flow_iter(ffb_ctx* c, FfbRing R, size_t plane, int rp, int w, int h, 
         else { nt = 128; u = 2; ho = 4; }
     }
     switch (nt * 100 + u * 10 + ho) {
-        case 12824:
-            switch (k.opt) {
-                case 1:  return launch_flow_iter_t<128, 2, 4, 4, 1>(c, a, npairs, k.sh, bytes);
-                case 2:  return launch_flow_iter_t<128, 2, 4, 4, 2>(c, a, npairs, k.sh, bytes);
-                case 3:  return launch_flow_iter_t<128, 2, 4, 4, 3>(c, a, npairs, k.sh, bytes);
-                default: return launch_flow_iter_t<128, 2, 4, 4, 0>(c, a, npairs, k.sh, bytes);
-            }
-        case 12828: return launch_flow_iter_t<128, 2, 4, 8>(c, a, npairs, k.sh, bytes);
-        case 12848: return launch_flow_iter_t<128, 4, 4, 8>(c, a, npairs, k.sh, bytes);
-        case 12844: return launch_flow_iter_t<128, 4, 4, 4>(c, a, npairs, k.sh, bytes);
-        case 16024: return launch_flow_iter_t<160, 2, 3, 4>(c, a, npairs, k.sh, bytes);
-        case 16028: return launch_flow_iter_t<160, 2, 3, 8>(c, a, npairs, k.sh, bytes);
-        case 25624: return launch_flow_iter_t<256, 2, 2, 4>(c, a, npairs, k.sh, bytes);
-        case 25628: return launch_flow_iter_t<256, 2, 2, 8>(c, a, npairs, k.sh, bytes);
         case 25648: return launch_flow_iter_t<256, 4, 2, 8>(c, a, npairs, k.sh, bytes);
-        case 25644: return launch_flow_iter_t<256, 4, 2, 4>(c, a, npairs, k.sh, bytes);
-        case 51248: return launch_flow_iter_t<512, 4, 1, 8>(c, a, npairs, k.sh, bytes);
-        case 51224: return launch_flow_iter_t<512, 2, 1, 4>(c, a, npairs, k.sh, bytes);
-        case 19248: return launch_flow_iter_t<192, 4, 2, 8>(c, a, npairs, k.sh, bytes);
-        case 9624:  return launch_flow_iter_t<96, 2, 5, 4>(c, a, npairs, k.sh, bytes);
+        case 12824: return launch_flow_iter_t<128, 2, 4, 4>(c, a, npairs, k.sh, bytes);
+        case 16024: return launch_flow_iter_t<160, 2, 3, 4>(c, a, npairs, k.sh, bytes);
         default: break;
     }
-    return fail(c, FFB_E_INVALID, "FFB_ITER_CFG: no k_flow_iter variant %dx%dx%d", nt, u, ho);
+    return fail(c, FFB_E_INVALID, "FFB_ITER_CFG: no k_flow_iter variant %dx%dx%d (compiled in: 256x4x8, 128x2x4, 160x2x4)", nt, u, ho);
 }
 
 // ------------------------------------------------------------------ geometry

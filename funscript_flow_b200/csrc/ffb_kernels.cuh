@@ -321,6 +321,7 @@ struct FfbPolyArgs {
     FfbRing dst;            // per frame-level: float4 [h][rp] (c0..c3) then float [h][rp] (c4); plane = rp * h
     size_t plane; int rp;
     FfbPolyConsts c;
+    int aligned2;           // every source row starts 8-byte aligned (k_polyexp2 loads column pairs)
 };
 
 constexpr int POLY_OW = 112;
@@ -426,6 +427,184 @@ __global__ void __launch_bounds__(256) k_polyexp(FfbPolyArgs a) {
                     dA[j] = make_float4(o[0][j], o[1][j], o[2][j], o[3][j]);
                     dB[j] = o[4][j];
                 }
+        }
+    }
+}
+
+// ======================================================================================
+// K2'  polynomial expansion with packed fp32 arithmetic (FFMA2 / FADD2 / FMUL2, sm_100)
+// ======================================================================================
+// k_polyexp is bound by instruction issue (70 % issue slots, ~100 fp32 instructions per output pixel), not by
+// memory.  Blackwell's packed instructions do two fp32 operations per lane and issue slot (IEEE per component,
+// same rounding as the scalar ones), so this variant keeps every operand as a natural register pair:
+//   phase V: a thread owns TWO ADJACENT COLUMNS (one aligned 8-byte load per row) of a quarter of the tile's
+//            rows (8 rows + 10 halo rows); the vertical sums of the column pair are packed operations on the
+//            loaded pairs, with no register shuffling.  They are written to shared memory transposed into
+//            ROW pairs: vrow2[3][POLY2_ROWS / 2][POLY_VP] holds float2 (row 2m, row 2m+1) per column, one
+//            16-byte store per (sum, row pair) and thread.
+//   phase H: a task = 4 adjacent output columns of one row pair: 8 aligned 16-byte shared loads per
+//            vertical sum (16 columns x 2 rows), the six horizontal sums of both rows with packed operations
+//            (every operand a (row 2m, row 2m+1) pair as loaded), the expansion of row 2m from the .x
+//            components and of row 2m+1 from the .y components.
+// Same operation order per component as k_polyexp (the tile starts one column further left so that column
+// pairs are 8-byte aligned).
+constexpr int POLY2_ROWS = 32;
+constexpr int POLY2_X0 = FFB_POLY_N + 1;       // tile column 0 = image column x0 - 6
+constexpr size_t POLY2_SMEM = sizeof(float2) * 3 * (POLY2_ROWS / 2) * POLY_VP;
+
+#ifdef FFB_EMU
+static inline float2 ffb_fma2(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+static inline float2 ffb_add2(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+static inline float2 ffb_sub2(float2 a, float2 b) { return make_float2(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y)); }
+static inline float2 ffb_mul2(float2 a, float2 b) { return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)); }
+#else
+__device__ __forceinline__ float2 ffb_fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 ffb_add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 ffb_sub2(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ float2 ffb_mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+#endif
+__device__ __forceinline__ float2 ffb_dup2(float v) { return make_float2(v, v); }
+
+__global__ void __launch_bounds__(256, 2) k_polyexp2(FfbPolyArgs a) {
+    constexpr int N = FFB_POLY_N;
+    constexpr int QR = POLY2_ROWS / 4;         // rows per thread in phase V
+    constexpr int NP = POLY2_ROWS / 2;         // row pairs per tile
+    FFB_DYN_SMEM(float2, vrow2);               // [3][NP][POLY_VP]
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * POLY_OW, y0 = blockIdx.y * POLY2_ROWS, f = blockIdx.z;
+    const float* src = a.src + (size_t)f * a.src_frame_stride;
+    const int w = a.w, h = a.h;
+    float2 g2[N + 1], xg2[N + 1], xxg2[N + 1];
+#pragma unroll
+    for (int k = 0; k <= N; ++k) { g2[k] = ffb_dup2(a.c.g[k]); xg2[k] = ffb_dup2(a.c.xg[k]); xxg2[k] = ffb_dup2(a.c.xxg[k]); }
+    // ---- phase V
+    {
+        const int cp = tid & 63, qr = tid >> 6;
+        const int xa = x0 - POLY2_X0 + 2 * cp;                    // image column of the pair's first element (even)
+        const bool vec = a.aligned2 && xa >= 0 && xa + 1 < w;     // interior: one aligned 8-byte load per row
+        const int xl = ffb_clampi(xa, 0, w - 1), xr = ffb_clampi(xa + 1, 0, w - 1);   // replicate border
+        const int yb = y0 + qr * QR;
+        float2 win[QR + 2 * N];
+#pragma unroll
+        for (int i = 0; i < QR + 2 * N; ++i) {
+            const float* row = src + (size_t)ffb_clampi(yb - N + i, 0, h - 1) * a.sp;
+            if (vec) win[i] = __ldg(reinterpret_cast<const float2*>(row + xa));
+            else win[i] = make_float2(__ldg(row + xl), __ldg(row + xr));
+        }
+#pragma unroll
+        for (int m = 0; m < QR / 2; ++m) {
+            float2 t[2][3];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int c = 2 * m + r + N;
+                float2 t0 = ffb_mul2(win[c], g2[0]);
+                float2 t1 = make_float2(0.f, 0.f), t2 = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int k = 1; k <= N; ++k) {
+                    const float2 up = win[c - k], dn = win[c + k];
+                    const float2 p = ffb_add2(up, dn);
+                    t0 = ffb_fma2(g2[k], p, t0);
+                    t1 = ffb_fma2(xg2[k], ffb_sub2(dn, up), t1);
+                    t2 = ffb_fma2(xxg2[k], p, t2);
+                }
+                t[r][0] = t0; t[r][1] = t1; t[r][2] = t2;
+            }
+            // (column pair) x (row pair) -> two (row pair) entries of adjacent columns: one 16-byte store per sum
+            const int rp = qr * (QR / 2) + m;
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                *reinterpret_cast<float4*>(vrow2 + (k * NP + rp) * POLY_VP + 2 * cp) =
+                    make_float4(t[0][k].x, t[1][k].x, t[0][k].y, t[1][k].y);
+        }
+    }
+    __syncthreads();
+    // ---- phase H
+    constexpr int QUADS = POLY_OW / 4;
+    float* dst0 = reinterpret_cast<float*>(ffb_ring_at(a.dst, f));
+    const float2 ig11 = ffb_dup2(a.c.ig11), ig03 = ffb_dup2(a.c.ig03), ig33 = ffb_dup2(a.c.ig33), ig55 = ffb_dup2(a.c.ig55);
+    for (int t = tid; t < QUADS * NP; t += 256) {
+        const int rp = t / QUADS, q = t - rp * QUADS;
+        const int x = x0 + 4 * q, y = y0 + 2 * rp;
+        if (x >= w || y >= h) continue;
+        float2 b1[4], b2[4], b3[4], b4[4], b5[4], b6[4];
+        float2 v[16];
+        auto load_plane = [&](int k) {
+            const float4* p4 = reinterpret_cast<const float4*>(vrow2 + (k * NP + rp) * POLY_VP + 4 * q);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 t4 = p4[j];
+                v[2 * j] = make_float2(t4.x, t4.y);
+                v[2 * j + 1] = make_float2(t4.z, t4.w);
+            }
+        };
+        load_plane(0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2* r0 = &v[j + POLY2_X0];
+            float2 s1 = ffb_mul2(r0[0], g2[0]), s2 = make_float2(0.f, 0.f), s4 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int k = 1; k <= N; ++k) {
+                const float2 pp = r0[k], mm = r0[-k];
+                const float2 tg = ffb_add2(pp, mm);
+                s1 = ffb_fma2(tg, g2[k], s1);
+                s4 = ffb_fma2(tg, xxg2[k], s4);
+                s2 = ffb_fma2(ffb_sub2(pp, mm), xg2[k], s2);
+            }
+            b1[j] = s1; b2[j] = s2; b4[j] = s4;
+        }
+        load_plane(1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2* r1 = &v[j + POLY2_X0];
+            float2 s3 = ffb_mul2(r1[0], g2[0]), s6 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int k = 1; k <= N; ++k) {
+                s3 = ffb_fma2(ffb_add2(r1[k], r1[-k]), g2[k], s3);
+                s6 = ffb_fma2(ffb_sub2(r1[k], r1[-k]), xg2[k], s6);
+            }
+            b3[j] = s3; b6[j] = s6;
+        }
+        load_plane(2);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2* r2 = &v[j + POLY2_X0];
+            float2 s5 = ffb_mul2(r2[0], g2[0]);
+#pragma unroll
+            for (int k = 1; k <= N; ++k) s5 = ffb_fma2(ffb_add2(r2[k], r2[-k]), g2[k], s5);
+            b5[j] = s5;
+        }
+        float2 o[5][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            o[0][j] = ffb_mul2(b3[j], ig11);
+            o[1][j] = ffb_mul2(b2[j], ig11);
+            o[2][j] = ffb_fma2(b1[j], ig03, ffb_mul2(b5[j], ig33));
+            o[3][j] = ffb_fma2(b1[j], ig03, ffb_mul2(b4[j], ig33));
+            o[4][j] = ffb_mul2(b6[j], ig55);
+        }
+        // expansion layout: float4 (d/dy, d/dx, yy, xx) per pixel, then a separate float plane for xy
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            if (y + r >= h) break;
+            const size_t pix = (size_t)(y + r) * a.rp + x;
+            float4* dA = reinterpret_cast<float4*>(dst0) + pix;
+            float* dB = dst0 + 4 * a.plane + pix;
+#define FFB_C(e) (r == 0 ? (e).x : (e).y)
+            if (x + 3 < w) {   // x % 4 == 0 and rows are 64-byte aligned: the four pixels are two aligned 32-byte halves
+                ffb_store_f8(reinterpret_cast<float*>(dA), make_float4(FFB_C(o[0][0]), FFB_C(o[1][0]), FFB_C(o[2][0]), FFB_C(o[3][0])),
+                             make_float4(FFB_C(o[0][1]), FFB_C(o[1][1]), FFB_C(o[2][1]), FFB_C(o[3][1])));
+                ffb_store_f8(reinterpret_cast<float*>(dA + 2), make_float4(FFB_C(o[0][2]), FFB_C(o[1][2]), FFB_C(o[2][2]), FFB_C(o[3][2])),
+                             make_float4(FFB_C(o[0][3]), FFB_C(o[1][3]), FFB_C(o[2][3]), FFB_C(o[3][3])));
+                *reinterpret_cast<float4*>(dB) = make_float4(FFB_C(o[4][0]), FFB_C(o[4][1]), FFB_C(o[4][2]), FFB_C(o[4][3]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (x + j < w) {
+                        dA[j] = make_float4(FFB_C(o[0][j]), FFB_C(o[1][j]), FFB_C(o[2][j]), FFB_C(o[3][j]));
+                        dB[j] = FFB_C(o[4][j]);
+                    }
+            }
+#undef FFB_C
         }
     }
 }
@@ -554,10 +733,6 @@ struct FfbIterArgs {
     const float2* up_src; size_t up_stride; int usp; int wc, hc;
 };
 
-// OPT bits of k_flow_iter (measured variants):
-constexpr int FFB_IT_STREAM = 1;     // R0 and flow-in loads do not allocate in L1 (they are used once per CTA)
-constexpr int FFB_IT_PREFETCH = 2;   // one thread bulk-prefetches the rows of step s + 4 into L2
-
 // Shared row buffer of the vertical sums, one row of NT positions per (buffer, row of the step, channel).
 // HO = 4: position p is stored at p.  HO = 8: a task reads the six 16-byte vectors 2g .. 2g+5 (g = task
 // index), i.e. lanes are 32 bytes apart and a quarter-warp would hit every bank twice; the even and the
@@ -590,38 +765,9 @@ struct FfbGather {
     int inside;
 };
 
-// global loads that do not allocate in L1 (streams that a CTA reads once)
-#ifdef FFB_EMU
-static inline float4 ffb_ldg_stream4(const float4* p) { return *p; }
-static inline float2 ffb_ldg_stream2(const float2* p) { return *p; }
-static inline float ffb_ldg_stream1(const float* p) { return *p; }
-static inline void ffb_prefetch_l2(const void*, unsigned) {}
-#else
-__device__ __forceinline__ float4 ffb_ldg_stream4(const float4* p) {
-    float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ float2 ffb_ldg_stream2(const float2* p) {
-    float2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ float ffb_ldg_stream1(const float* p) {
-    float v;
-    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
-    return v;
-}
-// bulk prefetch of `bytes` (multiple of 16) at a 16-byte aligned address into L2
-__device__ __forceinline__ void ffb_prefetch_l2(const void* p, unsigned bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-#endif
-
 // Expansion layout (written by k_polyexp): per frame-level a float4 image A[h][rp] holding
 // (d/dy, d/dx, yy, xx) per pixel followed by a float plane B[h][rp] holding xy.  A 2x2 bilinear
 // footprint is then 4 x 16-byte + 4 x 4-byte loads off two row addresses instead of 20 scalar loads.
-template <bool STREAM>
 __device__ __forceinline__ void ffb_gather_issue(const float4* __restrict__ A0, const float* __restrict__ B0,
                                                  const float4* __restrict__ A1, const float* __restrict__ B1,
                                                  int rp, int w, int h, int x, int y, float2 d, FfbGather& g) {
@@ -635,8 +781,8 @@ __device__ __forceinline__ void ffb_gather_issue(const float4* __restrict__ A0, 
     g.inside = ((unsigned)x1 < (unsigned)(w - 1)) && ((unsigned)y1 < (unsigned)(h - 1));
     const int xs = min(max(x1, 0), w - 2), ys = min(max(y1, 0), h - 2);
     const unsigned o0 = (unsigned)(y * rp + x), o1 = (unsigned)(ys * rp + xs);
-    const float4 q = STREAM ? ffb_ldg_stream4(A0 + o0) : __ldg(A0 + o0);
-    const float q4 = STREAM ? ffb_ldg_stream1(B0 + o0) : __ldg(B0 + o0);
+    const float4 q = __ldg(A0 + o0);
+    const float q4 = __ldg(B0 + o0);
     const float4 t00 = __ldg(A1 + o1);
     const float4 t01 = __ldg(A1 + o1 + 1);
     const float4 t10 = __ldg(A1 + o1 + rp);
@@ -712,13 +858,12 @@ __device__ __forceinline__ float2 ffb_solve(float s0, float s1, float s2, float 
     return o;
 }
 
-template <int NT, int U, int MINB, bool UP2X, int HO, int OPT>
+template <int NT, int U, int MINB, bool UP2X, int HO>
 __global__ void __launch_bounds__(NT, MINB) k_flow_iter(FfbIterArgs a) {
     static_assert(HO == 4 || HO == 8, "outputs per horizontal task");
     static_assert(U == 2 || U == 4, "rows per step");
     using HL = FfbHrowLayout<NT, HO>;
     constexpr int NB = U == 2 ? 2 : 1;               // row buffers
-    constexpr bool STREAM = (OPT & FFB_IT_STREAM) != 0;
     // dynamic shared memory (exceeds the 48 KB static limit): row buffer first (16-byte aligned), then the ring
     FFB_DYN_SMEM(float, smem_f);
     float* hrow = smem_f;                                               // [NB][U] rows of RSTRIDE floats: [5][PITCH]
@@ -878,33 +1023,10 @@ __global__ void __launch_bounds__(NT, MINB) k_flow_iter(FfbIterArgs a) {
                 db.y = (sy * (1.f - be1) + cy * be1) * 2.f;
             }
         } else if (fin) {
-            da = STREAM ? ffb_ldg_stream2(fin + (ya * a.fip + xc)) : __ldg(fin + (ya * a.fip + xc));
-            db = STREAM ? ffb_ldg_stream2(fin + (yb * a.fip + xc)) : __ldg(fin + (yb * a.fip + xc));
+            da = __ldg(fin + (ya * a.fip + xc));
+            db = __ldg(fin + (yb * a.fip + xc));
         } else {
             da = db = make_float2(0.f, 0.f);
-        }
-    };
-
-    // OPT & FFB_IT_PREFETCH: the first lane of the last warp asks L2 for the rows of step s + 4 (the expansion
-    // rows of both frames over the strip's columns, assuming the flow moves the footprint by less than 8
-    // pixels); requests that fall outside the image are clipped, not issued
-    auto prefetch_rows = [&](int s) {
-        if (!(OPT & FFB_IT_PREFETCH) || tid != NT - 32) return;
-        const int xa = max(xo0 - 2 * FFB_WIN_R - 1, 0) & ~3, xb = min(xo0 + a.SW + 2 * FFB_WIN_R + 1, w);
-        if (xb <= xa) return;
-        const unsigned n4 = (unsigned)(((xb - xa) + 3) & ~3);
-        const int ya = y0 - FFB_WIN_R + (s + 4) * U;
-#pragma unroll
-        for (int r = -1; r <= U; ++r) {
-            const int y = ya + r;
-            if (y < 0 || y >= h) continue;
-            const unsigned o = (unsigned)(y * a.rp + xa);
-            ffb_prefetch_l2(A1 + o, n4 * 16u);
-            ffb_prefetch_l2(B1 + o, n4 * 4u);
-            if (r >= 0 && r < U) {
-                ffb_prefetch_l2(A0 + o, n4 * 16u);
-                ffb_prefetch_l2(B0 + o, n4 * 4u);
-            }
         }
     };
 
@@ -913,24 +1035,26 @@ __global__ void __launch_bounds__(NT, MINB) k_flow_iter(FfbIterArgs a) {
 #pragma unroll
         for (int u = 0; u < U; u += 2) load_flow2(u, d[u], d[u + 1]);
     }
+    // issue the gather of feed rows s*U + hh, + 1 (20 independent loads)
+    auto issue_pair = [&](int s, int hh, FfbGather (&g)[2]) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int yc = ffb_clampi(y0 - FFB_WIN_R + s * U + hh + u, 0, h - 1);
+            ffb_gather_issue(A0, B0, A1, B1, a.rp, w, h, xc, yc, d[hh + u], g[u]);
+        }
+    };
     for (int s = 0; s < nsteps; ++s) {
         const int buf = NB == 2 ? (s & 1) : 0;
         // the horizontal phase of the previous step runs before this step's loads are issued
         // (lower register pressure; the other resident warps cover the load latency)
         if (s > 0) horizontal(s - 1, NB == 2 ? (buf ^ 1) : 0);
-        prefetch_rows(s);
+        FfbGather g[2];
+        if (live) issue_pair(s, 0, g);
 #pragma unroll
         for (int hh = 0; hh < U; hh += 2) {
             float vrow[2][5];
             if (live) {
-                // ---- issue the gather of rows hh, hh + 1 (20 independent loads), then the flow prefetch of step s+1
-                FfbGather g[2];
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int yc = ffb_clampi(y0 - FFB_WIN_R + s * U + hh + u, 0, h - 1);
-                    ffb_gather_issue<STREAM>(A0, B0, A1, B1, a.rp, w, h, xc, yc, d[hh + u], g[u]);
-                }
-                load_flow2((s + 1) * U + hh, dn[hh], dn[hh + 1]);
+                load_flow2((s + 1) * U + hh, dn[hh], dn[hh + 1]);      // flow prefetch of step s+1 (feeds its gather addresses)
                 // ---- matrices + vertical running sums (Kahan-compensated add of  new - leaving)
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
@@ -961,6 +1085,7 @@ __global__ void __launch_bounds__(NT, MINB) k_flow_iter(FfbIterArgs a) {
                 for (int u = 0; u < 2; ++u)
 #pragma unroll
                     for (int c = 0; c < 5; ++c) hrow[(buf * U + hh + u) * HL::RSTRIDE + c * HL::PITCH + hpos] = vrow[u][c];
+                if (hh + 2 < U) issue_pair(s, hh + 2, g);      // (issuing these before the barrier spills: -17 %)
             }
         }
         __syncthreads();

@@ -3,9 +3,10 @@
 
 The .pyw is parsed with ``ast``; only whitelisted top-level definitions are kept and executed
 in a namespace seeded with the stdlib / NumPy / cv2 names they use.  Nothing is copied into the
-repo: the source is read where it lies (``/root/reference``).  That directory exists only in the
-build container, so everything derived from it that must travel to the GPU box is stored as
-golden vectors under ``tests/golden/`` by ``tests/golden/make_golden.py``.
+repo's history: the source is read where it lies (``/root/reference``, which exists only in the build
+container) or from the git-ignored staging copy ``baseline/_ref/FunscriptFlow.pyw`` that travels to the GPU
+box for the reference arm of bench.py.  What the tests need from it is stored as golden vectors under
+``tests/golden/`` by ``tests/golden/make_golden.py``.
 """
 from __future__ import annotations
 
@@ -14,7 +15,24 @@ import os
 import sys
 import types
 
-REFERENCE_PYW = os.environ.get("FFB_REFERENCE_PYW", "/root/reference/FunscriptFlow.pyw")
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# Where the unmodified FunscriptFlow.pyw may lie: the read-only reference checkout of the build container, or the
+# git-ignored staging copy baseline/_ref/ that __graft_entry__.build() makes from it so that the file travels to
+# the GPU box with the repo snapshot (it is never committed: .gitignore lists baseline/_ref/).
+STAGED_PYW = os.path.join(_ROOT, "baseline", "_ref", "FunscriptFlow.pyw")
+_CANDIDATES = [os.environ.get("FFB_REFERENCE_PYW", ""), "/root/reference/FunscriptFlow.pyw", STAGED_PYW]
+REFERENCE_PYW = next((p for p in _CANDIDATES if p and os.path.isfile(p)), "/root/reference/FunscriptFlow.pyw")
+
+
+def stage(source: str = "/root/reference/FunscriptFlow.pyw") -> bool:
+    """Copy the reference file, byte for byte, into baseline/_ref/ (git-ignored).  Returns True when the staged
+    copy exists afterwards."""
+    import shutil
+    if os.path.isfile(source):
+        os.makedirs(os.path.dirname(STAGED_PYW), exist_ok=True)
+        if not os.path.isfile(STAGED_PYW) or open(source, "rb").read() != open(STAGED_PYW, "rb").read():
+            shutil.copyfile(source, STAGED_PYW)
+    return os.path.isfile(STAGED_PYW)
 
 _KEEP = {
     "max_divergence", "radial_motion_weighted", "precompute_flow_info", "precompute_flow_info_gpu",
