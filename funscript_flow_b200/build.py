@@ -24,7 +24,7 @@ DEPS = SOURCES + [os.path.join(CSRC, "ffb_kernels.cuh"), os.path.join(CSRC, "ffb
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function",
+    "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function,-pthread",
     "--expt-relaxed-constexpr",
     "-shared", "-cudart", "shared",
 ]

@@ -19,6 +19,7 @@
 #include <limits>
 #include <set>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -253,6 +254,7 @@ struct ffb_ctx {
     cudaEvent_t phase_rec_e1 = nullptr;
     bool prof_open = false;                              // a per-launch record is waiting for its end event
     int flow_streams = 2;
+    int copy_threads = 4;                                // host threads that stage pageable frames into pinned memory
     int64_t launches = 0;
     cudaEvent_t timers[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
@@ -418,25 +420,19 @@ int launch_polyexp(ffb_ctx* c, const float* src, size_t src_stride, int sp, int 
     FfbPolyArgs a;
     a.src = src; a.src_frame_stride = src_stride; a.sp = sp; a.w = w; a.h = h;
     a.dst = dst; a.plane = plane; a.rp = rp; a.c = c->poly;
-    a.aligned2 = (sp % 2 == 0) && (src_stride % 2 == 0) && ((uintptr_t)src % 8 == 0);
     // the kernel stores two pixels (32 bytes) of the float4 image per instruction
     if (rp % 4 != 0 || ((uintptr_t)dst.base | (uintptr_t)dst.stride) % 32 != 0)
         return fail(c, FFB_E_INVALID, "expansion output is not 32-byte aligned (pitch %d, stride %zu)", rp, dst.stride);
     if (!c->attr_poly) {
         CK(c, cudaFuncSetAttribute(k_polyexp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POLY_SMEM));
-        CK(c, cudaFuncSetAttribute(k_polyexp2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POLY2_SMEM));
         c->attr_poly = true;
     }
-    // FFB_POLY=0: the scalar kernel (kept for A/B runs); default: two rows at a time with packed fp32 arithmetic
-    const bool packed = !(getenv("FFB_POLY") && atoi(getenv("FFB_POLY")) == 0);
+    // (a variant with packed fp32 arithmetic -- FFMA2 / FADD2 / FMUL2 on row pairs -- was measured in round 2: 4.60 ms
+    // against 3.92 ms per 257 1080p frames for this scalar kernel; the packed instructions issue at half rate and the
+    // 114 registers they need halve the occupancy.  profiles/r2_other_kernels.txt)
+    dim3 grid((w + POLY_OW - 1) / POLY_OW, (h + POLY_ROWS - 1) / POLY_ROWS, nframes);
     prof_begin(c, FFB_K_POLYEXP, (double)nframes * 24.0 * w * h);
-    if (packed) {
-        dim3 grid((w + POLY_OW - 1) / POLY_OW, (h + POLY2_ROWS - 1) / POLY2_ROWS, nframes);
-        FFB_LAUNCH(k_polyexp2, grid, dim3(256), POLY2_SMEM, c->s_comp, a);
-    } else {
-        dim3 grid((w + POLY_OW - 1) / POLY_OW, (h + POLY_ROWS - 1) / POLY_ROWS, nframes);
-        FFB_LAUNCH(k_polyexp, grid, dim3(256), POLY_SMEM, c->s_comp, a);
-    }
+    FFB_LAUNCH(k_polyexp, grid, dim3(256), POLY_SMEM, c->s_comp, a);
     prof_end(c);
     CKL(c);
     return FFB_OK;
@@ -966,6 +962,33 @@ int radial_range(ffb_ctx* c, int j0, int j1, int n, bool smooth = true) {
     return FFB_OK;
 }
 
+// Pageable frames reach the pinned staging buffer through host memcpy: one thread moves ~7 GB/s, less than the
+// GPU consumes at 1080p (a 257-frame bracket is 533 MB every 36 ms), so large copies are cut into row ranges and
+// moved by a few threads (FFB_COPY_THREADS, default 4; they inherit the caller's CPU affinity, i.e. the NUMA
+// node of the GPU when the process was bound to it).  n frames of `rows` rows of `row` bytes each.
+void copy_frames(uint8_t* dst, size_t dst_frame, const uint8_t* src, size_t src_frame, size_t src_pitch, int n, int rows,
+                 size_t row, int max_threads) {
+    const long long total_rows = (long long)n * rows;
+    auto work = [=](long long r0, long long r1) {
+        while (r0 < r1) {
+            const int f = (int)(r0 / rows), a = (int)(r0 % rows);
+            const int b = (int)((r1 - (long long)f * rows) < rows ? (r1 - (long long)f * rows) : rows);
+            const uint8_t* s0 = src + (size_t)f * src_frame + (size_t)a * src_pitch;
+            uint8_t* d0 = dst + (size_t)f * dst_frame + (size_t)a * row;
+            if (src_pitch == row) memcpy(d0, s0, (size_t)(b - a) * row);
+            else for (int y = 0; y < b - a; ++y) memcpy(d0 + (size_t)y * row, s0 + (size_t)y * src_pitch, row);
+            r0 += b - a;
+        }
+    };
+    int t = (int)(((size_t)total_rows * row) >> 21);          // at least 2 MB per thread
+    if (t > max_threads) t = max_threads;
+    if (t <= 1) { work(0, total_rows); return; }
+    std::vector<std::thread> pool;
+    for (int i = 1; i < t; ++i) pool.emplace_back(work, total_rows * i / t, total_rows * (i + 1) / t);
+    work(0, total_rows / t);
+    for (std::thread& th : pool) th.join();
+}
+
 enum PtrKind { PTR_PAGEABLE, PTR_PINNED, PTR_DEVICE };
 PtrKind classify(const void* p) {
     cudaPointerAttributes at;
@@ -989,12 +1012,7 @@ int process_batch(ffb_ctx* c, const uint8_t* frames, int nb, size_t pitch, size_
         CK(c, cudaStreamWaitEvent(c->s_copy, c->ev_expand[b], 0));
         if (kind == PTR_PAGEABLE) {
             CK(c, cudaEventSynchronize(c->ev_h2d[b]));   // previous DMA out of h_pin[b] finished
-            for (int f = 0; f < nb; ++f) {
-                const uint8_t* s = frames + (size_t)f * stride;
-                uint8_t* d = c->h_pin[b] + (size_t)f * fbytes;
-                if (pitch == (size_t)c->W) memcpy(d, s, fbytes);
-                else for (int y = 0; y < c->H; ++y) memcpy(d + (size_t)y * c->W, s + (size_t)y * pitch, c->W);
-            }
+            copy_frames(c->h_pin[b], fbytes, frames, stride, pitch, nb, c->H, (size_t)c->W, c->copy_threads);
             CK(c, cudaMemcpyAsync(c->d_u8[b], c->h_pin[b], (size_t)nb * fbytes, cudaMemcpyHostToDevice, c->s_copy));
         } else if (pitch == (size_t)c->W && stride == fbytes) {
             CK(c, cudaMemcpyAsync(c->d_u8[b], frames, (size_t)nb * fbytes, cudaMemcpyHostToDevice, c->s_copy));
@@ -1182,6 +1200,7 @@ int ffb_create(int device, ffb_ctx** out) {
     c->launch_stream = c->s_comp;
     c->aux_stream = c->s_comp;
     if (const char* e = getenv("FFB_FLOW_STREAMS")) c->flow_streams = atoi(e);
+    if (const char* e = getenv("FFB_COPY_THREADS")) { const int v = atoi(e); if (v >= 1 && v <= 64) c->copy_threads = v; }
     for (int b = 0; b < 2; ++b) {
         cudaEventCreateWithFlags(&c->ev_h2d[b], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&c->ev_expand[b], cudaEventDisableTiming);
@@ -1749,12 +1768,7 @@ int ffb_bracket_push_bgr(ffb_ctx* c, const uint8_t* bgr, int n, size_t pitch, si
             CK(c, cudaStreamWaitEvent(c->s_copy, c->ev_pre[cb], 0));      // kernel that last read d_color[cb]
             if (kind == PTR_PAGEABLE) {
                 CK(c, cudaEventSynchronize(c->ev_ch2d[cb]));              // DMA that last read h_color[cb]
-                for (int f = 0; f < m; ++f) {
-                    const uint8_t* s0 = src + (size_t)f * stride;
-                    uint8_t* d0 = c->h_color[cb] + (size_t)f * fbytes;
-                    if (pitch == row) memcpy(d0, s0, fbytes);
-                    else for (int y = 0; y < pp.H; ++y) memcpy(d0 + (size_t)y * row, s0 + (size_t)y * pitch, row);
-                }
+                copy_frames(c->h_color[cb], fbytes, src, stride, pitch, m, pp.H, row, c->copy_threads);
                 CK(c, cudaMemcpyAsync(c->d_color[cb], c->h_color[cb], (size_t)m * fbytes, cudaMemcpyHostToDevice, c->s_copy));
             } else if (pitch == row && stride == fbytes) {
                 CK(c, cudaMemcpyAsync(c->d_color[cb], src, (size_t)m * fbytes, cudaMemcpyHostToDevice, c->s_copy));

@@ -321,7 +321,6 @@ struct FfbPolyArgs {
     FfbRing dst;            // per frame-level: float4 [h][rp] (c0..c3) then float [h][rp] (c4); plane = rp * h
     size_t plane; int rp;
     FfbPolyConsts c;
-    int aligned2;           // every source row starts 8-byte aligned (k_polyexp2 loads column pairs)
 };
 
 constexpr int POLY_OW = 112;
@@ -427,184 +426,6 @@ __global__ void __launch_bounds__(256) k_polyexp(FfbPolyArgs a) {
                     dA[j] = make_float4(o[0][j], o[1][j], o[2][j], o[3][j]);
                     dB[j] = o[4][j];
                 }
-        }
-    }
-}
-
-// ======================================================================================
-// K2'  polynomial expansion with packed fp32 arithmetic (FFMA2 / FADD2 / FMUL2, sm_100)
-// ======================================================================================
-// k_polyexp is bound by instruction issue (70 % issue slots, ~100 fp32 instructions per output pixel), not by
-// memory.  Blackwell's packed instructions do two fp32 operations per lane and issue slot (IEEE per component,
-// same rounding as the scalar ones), so this variant keeps every operand as a natural register pair:
-//   phase V: a thread owns TWO ADJACENT COLUMNS (one aligned 8-byte load per row) of a quarter of the tile's
-//            rows (8 rows + 10 halo rows); the vertical sums of the column pair are packed operations on the
-//            loaded pairs, with no register shuffling.  They are written to shared memory transposed into
-//            ROW pairs: vrow2[3][POLY2_ROWS / 2][POLY_VP] holds float2 (row 2m, row 2m+1) per column, one
-//            16-byte store per (sum, row pair) and thread.
-//   phase H: a task = 4 adjacent output columns of one row pair: 8 aligned 16-byte shared loads per
-//            vertical sum (16 columns x 2 rows), the six horizontal sums of both rows with packed operations
-//            (every operand a (row 2m, row 2m+1) pair as loaded), the expansion of row 2m from the .x
-//            components and of row 2m+1 from the .y components.
-// Same operation order per component as k_polyexp (the tile starts one column further left so that column
-// pairs are 8-byte aligned).
-constexpr int POLY2_ROWS = 32;
-constexpr int POLY2_X0 = FFB_POLY_N + 1;       // tile column 0 = image column x0 - 6
-constexpr size_t POLY2_SMEM = sizeof(float2) * 3 * (POLY2_ROWS / 2) * POLY_VP;
-
-#ifdef FFB_EMU
-static inline float2 ffb_fma2(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
-static inline float2 ffb_add2(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
-static inline float2 ffb_sub2(float2 a, float2 b) { return make_float2(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y)); }
-static inline float2 ffb_mul2(float2 a, float2 b) { return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)); }
-#else
-__device__ __forceinline__ float2 ffb_fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
-__device__ __forceinline__ float2 ffb_add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
-__device__ __forceinline__ float2 ffb_sub2(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
-__device__ __forceinline__ float2 ffb_mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
-#endif
-__device__ __forceinline__ float2 ffb_dup2(float v) { return make_float2(v, v); }
-
-__global__ void __launch_bounds__(256, 2) k_polyexp2(FfbPolyArgs a) {
-    constexpr int N = FFB_POLY_N;
-    constexpr int QR = POLY2_ROWS / 4;         // rows per thread in phase V
-    constexpr int NP = POLY2_ROWS / 2;         // row pairs per tile
-    FFB_DYN_SMEM(float2, vrow2);               // [3][NP][POLY_VP]
-    const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * POLY_OW, y0 = blockIdx.y * POLY2_ROWS, f = blockIdx.z;
-    const float* src = a.src + (size_t)f * a.src_frame_stride;
-    const int w = a.w, h = a.h;
-    float2 g2[N + 1], xg2[N + 1], xxg2[N + 1];
-#pragma unroll
-    for (int k = 0; k <= N; ++k) { g2[k] = ffb_dup2(a.c.g[k]); xg2[k] = ffb_dup2(a.c.xg[k]); xxg2[k] = ffb_dup2(a.c.xxg[k]); }
-    // ---- phase V
-    {
-        const int cp = tid & 63, qr = tid >> 6;
-        const int xa = x0 - POLY2_X0 + 2 * cp;                    // image column of the pair's first element (even)
-        const bool vec = a.aligned2 && xa >= 0 && xa + 1 < w;     // interior: one aligned 8-byte load per row
-        const int xl = ffb_clampi(xa, 0, w - 1), xr = ffb_clampi(xa + 1, 0, w - 1);   // replicate border
-        const int yb = y0 + qr * QR;
-        float2 win[QR + 2 * N];
-#pragma unroll
-        for (int i = 0; i < QR + 2 * N; ++i) {
-            const float* row = src + (size_t)ffb_clampi(yb - N + i, 0, h - 1) * a.sp;
-            if (vec) win[i] = __ldg(reinterpret_cast<const float2*>(row + xa));
-            else win[i] = make_float2(__ldg(row + xl), __ldg(row + xr));
-        }
-#pragma unroll
-        for (int m = 0; m < QR / 2; ++m) {
-            float2 t[2][3];
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int c = 2 * m + r + N;
-                float2 t0 = ffb_mul2(win[c], g2[0]);
-                float2 t1 = make_float2(0.f, 0.f), t2 = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int k = 1; k <= N; ++k) {
-                    const float2 up = win[c - k], dn = win[c + k];
-                    const float2 p = ffb_add2(up, dn);
-                    t0 = ffb_fma2(g2[k], p, t0);
-                    t1 = ffb_fma2(xg2[k], ffb_sub2(dn, up), t1);
-                    t2 = ffb_fma2(xxg2[k], p, t2);
-                }
-                t[r][0] = t0; t[r][1] = t1; t[r][2] = t2;
-            }
-            // (column pair) x (row pair) -> two (row pair) entries of adjacent columns: one 16-byte store per sum
-            const int rp = qr * (QR / 2) + m;
-#pragma unroll
-            for (int k = 0; k < 3; ++k)
-                *reinterpret_cast<float4*>(vrow2 + (k * NP + rp) * POLY_VP + 2 * cp) =
-                    make_float4(t[0][k].x, t[1][k].x, t[0][k].y, t[1][k].y);
-        }
-    }
-    __syncthreads();
-    // ---- phase H
-    constexpr int QUADS = POLY_OW / 4;
-    float* dst0 = reinterpret_cast<float*>(ffb_ring_at(a.dst, f));
-    const float2 ig11 = ffb_dup2(a.c.ig11), ig03 = ffb_dup2(a.c.ig03), ig33 = ffb_dup2(a.c.ig33), ig55 = ffb_dup2(a.c.ig55);
-    for (int t = tid; t < QUADS * NP; t += 256) {
-        const int rp = t / QUADS, q = t - rp * QUADS;
-        const int x = x0 + 4 * q, y = y0 + 2 * rp;
-        if (x >= w || y >= h) continue;
-        float2 b1[4], b2[4], b3[4], b4[4], b5[4], b6[4];
-        float2 v[16];
-        auto load_plane = [&](int k) {
-            const float4* p4 = reinterpret_cast<const float4*>(vrow2 + (k * NP + rp) * POLY_VP + 4 * q);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float4 t4 = p4[j];
-                v[2 * j] = make_float2(t4.x, t4.y);
-                v[2 * j + 1] = make_float2(t4.z, t4.w);
-            }
-        };
-        load_plane(0);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float2* r0 = &v[j + POLY2_X0];
-            float2 s1 = ffb_mul2(r0[0], g2[0]), s2 = make_float2(0.f, 0.f), s4 = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int k = 1; k <= N; ++k) {
-                const float2 pp = r0[k], mm = r0[-k];
-                const float2 tg = ffb_add2(pp, mm);
-                s1 = ffb_fma2(tg, g2[k], s1);
-                s4 = ffb_fma2(tg, xxg2[k], s4);
-                s2 = ffb_fma2(ffb_sub2(pp, mm), xg2[k], s2);
-            }
-            b1[j] = s1; b2[j] = s2; b4[j] = s4;
-        }
-        load_plane(1);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float2* r1 = &v[j + POLY2_X0];
-            float2 s3 = ffb_mul2(r1[0], g2[0]), s6 = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int k = 1; k <= N; ++k) {
-                s3 = ffb_fma2(ffb_add2(r1[k], r1[-k]), g2[k], s3);
-                s6 = ffb_fma2(ffb_sub2(r1[k], r1[-k]), xg2[k], s6);
-            }
-            b3[j] = s3; b6[j] = s6;
-        }
-        load_plane(2);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float2* r2 = &v[j + POLY2_X0];
-            float2 s5 = ffb_mul2(r2[0], g2[0]);
-#pragma unroll
-            for (int k = 1; k <= N; ++k) s5 = ffb_fma2(ffb_add2(r2[k], r2[-k]), g2[k], s5);
-            b5[j] = s5;
-        }
-        float2 o[5][4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            o[0][j] = ffb_mul2(b3[j], ig11);
-            o[1][j] = ffb_mul2(b2[j], ig11);
-            o[2][j] = ffb_fma2(b1[j], ig03, ffb_mul2(b5[j], ig33));
-            o[3][j] = ffb_fma2(b1[j], ig03, ffb_mul2(b4[j], ig33));
-            o[4][j] = ffb_mul2(b6[j], ig55);
-        }
-        // expansion layout: float4 (d/dy, d/dx, yy, xx) per pixel, then a separate float plane for xy
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            if (y + r >= h) break;
-            const size_t pix = (size_t)(y + r) * a.rp + x;
-            float4* dA = reinterpret_cast<float4*>(dst0) + pix;
-            float* dB = dst0 + 4 * a.plane + pix;
-#define FFB_C(e) (r == 0 ? (e).x : (e).y)
-            if (x + 3 < w) {   // x % 4 == 0 and rows are 64-byte aligned: the four pixels are two aligned 32-byte halves
-                ffb_store_f8(reinterpret_cast<float*>(dA), make_float4(FFB_C(o[0][0]), FFB_C(o[1][0]), FFB_C(o[2][0]), FFB_C(o[3][0])),
-                             make_float4(FFB_C(o[0][1]), FFB_C(o[1][1]), FFB_C(o[2][1]), FFB_C(o[3][1])));
-                ffb_store_f8(reinterpret_cast<float*>(dA + 2), make_float4(FFB_C(o[0][2]), FFB_C(o[1][2]), FFB_C(o[2][2]), FFB_C(o[3][2])),
-                             make_float4(FFB_C(o[0][3]), FFB_C(o[1][3]), FFB_C(o[2][3]), FFB_C(o[3][3])));
-                *reinterpret_cast<float4*>(dB) = make_float4(FFB_C(o[4][0]), FFB_C(o[4][1]), FFB_C(o[4][2]), FFB_C(o[4][3]));
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (x + j < w) {
-                        dA[j] = make_float4(FFB_C(o[0][j]), FFB_C(o[1][j]), FFB_C(o[2][j]), FFB_C(o[3][j]));
-                        dB[j] = FFB_C(o[4][j]);
-                    }
-            }
-#undef FFB_C
         }
     }
 }

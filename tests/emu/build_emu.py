@@ -17,7 +17,7 @@ DEPS = [os.path.join(CSRC, f) for f in ("ffb_api.cu", "ffb_kernels.cuh", "ffb_co
 def build(force: bool = False) -> str:
     if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in DEPS):
         return LIB
-    cmd = ["g++", "-x", "c++", "-std=c++17", "-O2", "-g", "-fPIC", "-shared", "-DFFB_EMU", "-mfma", "-ffp-contract=fast",
+    cmd = ["g++", "-x", "c++", "-std=c++17", "-O2", "-g", "-fPIC", "-shared", "-pthread", "-DFFB_EMU", "-mfma", "-ffp-contract=fast",
            "-Wall", "-Wno-unused-function", "-Wno-unused-variable", "-Wno-unknown-pragmas",
            "-I", HERE, "-I", CSRC, "-I", os.path.join(ROOT, "include"),
            "-o", LIB, os.path.join(CSRC, "ffb_api.cu")]

@@ -14,7 +14,8 @@ Files written
   pairs.npz             small frame pairs + the reference precompute_flow_info() outputs (incl. cv2 flow)
   bracket.npz           a 28-frame 128x96 clip with one hard cut + the reference bracket loop's outputs
   postproc.json         per-pair scalar series + the actions the reference's post-processing emits
-  video_c1.json         actions of the reference's process_video() on the C1-style FFV1 clip
+  video_c1.json         actions of the reference's process_video() on the C1 clip (640x360, 300 frames, FFV1)
+  video_multibracket.json   the same for a clip cut into three brackets (batch_size=30), prefetch race neutralised
 """
 from __future__ import annotations
 
@@ -101,12 +102,28 @@ def main():
                 lst.append(infos[j + i]["pos_center"])
         centers.append(np.mean(np.array(lst), axis=0))
     scal = [ref.radial_motion_weighted(i["flow"], centers[j], i["cut"], False) for j, i in enumerate(infos)]
+    # The clip is only a valid golden for the CENTRES when every implementation must find the same argmax: the
+    # reference's own top-1 / top-2 gap of |div| has to be far above the ~1e-6 px by which flow fields of different
+    # (correct) implementations differ, and the NumPy restatement has to agree with cv2 on every centre.  The tests
+    # then assert the centres, the smoothed centres and the scalars unconditionally.
+    from oracle import farneback_np as fb, motion_np as mo
+    gaps = []
+    for j, i in enumerate(infos):
+        d = np.abs(mo.divergence_field(i["flow"]))
+        flat = int(np.argmax(d))
+        top1 = float(d.flat[flat])
+        d.flat[flat] = -1.0
+        gaps.append(top1 - float(d.max()))
+        ox, oy, _ = mo.max_divergence(fb.farneback(frames[j], frames[j + 1]))
+        assert (int(ox), int(oy)) == tuple(int(v) for v in i["pos_center"]), ("oracle and cv2 disagree on the centre of pair", j)
+    assert min(gaps) >= 3e-4, ("bracket clip lost its argmax margin", min(gaps))
     np.savez_compressed(
         os.path.join(HERE, "bracket.npz"), frames=frames, cut_threshold=np.float64(2.0),
         centers_raw=np.array([i["pos_center"] for i in infos], dtype=np.int64), centers=np.array(centers),
         val=np.array([i["val_pos"] for i in infos], dtype=np.float32),
         mean_mag=np.array([i["mean_mag"] for i in infos], dtype=np.float32),
-        cut=np.array([i["cut"] for i in infos], dtype=bool), scalar=np.array(scal, dtype=np.float64))
+        cut=np.array([i["cut"] for i in infos], dtype=bool), scalar=np.array(scal, dtype=np.float64),
+        argmax_gap=np.array(gaps, dtype=np.float64))
 
     # ---- 4. post-processing known answers (reference statements F:1266-1390)
     pp = ref_loader.postproc_function(ref)
@@ -125,7 +142,7 @@ def main():
     json.dump({"meta": meta, "cases": cases}, open(os.path.join(HERE, "postproc.json"), "w"))
 
     # ---- 5. the reference's process_video end to end on a C1-style clip (single bracket => no prefetch race)
-    spec = ClipSpec(640, 360, 120, seed=0, amplitude=0.15, period=30.0)
+    spec = ClipSpec(640, 360, 300, seed=0, amplitude=0.15, period=30.0)      # config C1 as BASELINE.json states it: 300 frames
     clip = ClipGenerator(spec).stack()
     with tempfile.TemporaryDirectory() as td:
         path = os.path.join(td, "c1.avi")
@@ -137,14 +154,54 @@ def main():
         assert not err, logs
         acts = json.load(open(os.path.join(td, "c1.funscript")))["actions"]
         # the per-pair series the reference computed on the decoded 256x256 frames (for diagnosis)
-        frames = ref.fetch_frames_optimized(path, list(range(120)), settings)
+        frames = ref.fetch_frames_optimized(path, list(range(300)), settings)
         infos = [ref.precompute_wrapper(p, settings) for p in zip(frames[:-1], frames[1:])]
-    json.dump({"meta": meta, "spec": {"width": 640, "height": 360, "n_frames": 120, "seed": 0, "amplitude": 0.15,
+    json.dump({"meta": meta, "spec": {"width": 640, "height": 360, "n_frames": 300, "seed": 0, "amplitude": 0.15,
                                       "period": 30.0, "fps": 30.0},
                "settings": settings, "actions": acts,
                "centers_raw": [[int(i["pos_center"][0]), int(i["pos_center"][1])] for i in infos],
                "mean_mag": [float(i["mean_mag"]) for i in infos]},
               open(os.path.join(HERE, "video_c1.json"), "w"))
+    # ---- 6. several brackets through the reference's process_video with its prefetch race neutralised (SURVEY Q3,
+    # F:1155-1185): the real threading.Thread is replaced by a stand-in whose start() runs the prefetch synchronously
+    # and whose is_alive() answers True, so that F:1157-1161 pops exactly the frames the prefetch just put -- the
+    # semantics the code intends (every bracket computed on its own frames).  Nothing else of the reference changes.
+    import types
+
+    class _SyncThread:
+        def __init__(self, target=None, args=(), kwargs=None, **_):
+            self._target, self._args, self._kwargs = target, args, kwargs or {}
+
+        def start(self):
+            self._target(*self._args, **self._kwargs)
+
+        def is_alive(self):
+            return True
+
+        def join(self, timeout=None):
+            return None
+    real_threading = ref.threading
+    ref.threading = types.SimpleNamespace(Thread=_SyncThread, Lock=real_threading.Lock, Event=real_threading.Event)
+    try:
+        spec = ClipSpec(640, 360, 75, seed=4, amplitude=0.2, period=24.0)
+        clip = ClipGenerator(spec).stack()
+        with tempfile.TemporaryDirectory() as td:
+            path = os.path.join(td, "mb.avi")
+            write_video(path, clip, 30.0)
+            settings = {"threads": 1, "detrend_window": 2.0, "norm_window": 3.0, "batch_size": 30, "overwrite": True,
+                        "vr_mode": False, "pov_mode": False, "keyframe_reduction": True, "backend": "CPU"}
+            logs = []
+            err = ref.process_video(path, settings, logs.append)
+            assert not err, logs
+            acts = json.load(open(os.path.join(td, "mb.funscript")))["actions"]
+    finally:
+        ref.threading = real_threading
+    json.dump({"meta": meta, "spec": {"width": 640, "height": 360, "n_frames": 75, "seed": 4, "amplitude": 0.2, "period": 24.0,
+                                      "fps": 30.0},
+               "settings": settings, "actions": acts, "brackets": [[0, 30], [30, 60], [60, 75]],
+               "note": "reference process_video with batch_size=30 (brackets of 30, 30 and 15 frames: 29 + 29 + 14 pairs, none "
+                       "across a bracket boundary), prefetch thread run synchronously (race-neutralised, SURVEY Q3)"},
+              open(os.path.join(HERE, "video_multibracket.json"), "w"))
     print("golden vectors written to", HERE)
 
 

@@ -201,22 +201,58 @@ def check_golden_bracket(ctx, golden_dir, batch_frames=5):
     assert np.array_equal(r["cut"], g["cut"]), "scene-cut flags differ"
     assert np.allclose(r["mean_mag"], g["mean_mag"], rtol=MEAN_MAG_RTOL, atol=MEAN_MAG_ATOL)
     import cv2
-    exact = 0
+    guarded = 0
     for j in range(n):
         flow = cv2.calcOpticalFlowFarneback(frames[j], frames[j + 1], None, 0.5, 3, 15, 3, 5, 1.2, 0)
         gap = assert_argmax((r["cx"][j], r["cy"][j]), r["val"][j], flow, f"pair {j}")
-        exact += gap >= ARGMAX_MARGIN
-        # scalar parity is asserted with the *device's* smoothed centre against the oracle formula,
-        # and against the recorded reference value when all centres in its window agree
+        guarded += gap < ARGMAX_MARGIN
+        # scalar parity with the *device's* smoothed centre against the oracle formula on cv2's flow
         ref_local = mo.radial_motion_weighted(flow, r["centers"][j], bool(g["cut"][j]))
         assert abs(r["scalar"][j] - ref_local) <= SCALAR_RTOL * abs(ref_local) + scalar_tol(flow, r["centers"][j]), j
-    same_centres = np.all(np.stack([r["cx"], r["cy"]], 1) == g["centers_raw"], axis=1)
-    assert exact >= n // 2, "test clip lost its argmax margin"
-    if same_centres.all():
-        assert np.allclose(r["centers"], g["centers"], rtol=0, atol=1e-12)
-        assert np.allclose(r["scalar"], g["scalar"], rtol=SCALAR_RTOL, atol=1e-6)
-    assert np.array_equal(r["centers"], api.smooth_centers(np.stack([r["cx"], r["cy"]], 1)))
+    # The generating script asserted that every pair of this clip has an argmax margin >= 3e-4 in the reference and
+    # that cv2 and the NumPy restatement agree on every centre, so nothing here is conditional: raw centres, smoothed
+    # centres (A5, F:1201-1214) and scalars must equal what the reference's functions produced.
+    print(f"golden bracket: {guarded} of {n} pairs fell under the {ARGMAX_MARGIN:g} argmax margin guard "
+          f"(smallest recorded margin {float(g['argmax_gap'].min()):.2e})")
+    assert guarded == 0, "the golden clip lost its argmax margin"
+    assert np.array_equal(np.stack([r["cx"], r["cy"]], 1), g["centers_raw"]), "raw centres differ from the reference's"
+    assert np.array_equal(r["centers"], mo.smooth_centers(np.stack([r["cx"], r["cy"]], 1))), "A5: smoothed centres differ from the oracle"
+    assert np.allclose(r["centers"], g["centers"], rtol=0, atol=1e-12)
+    assert np.allclose(r["scalar"], g["scalar"], rtol=SCALAR_RTOL, atol=1e-6)
     return r
+
+
+def check_bracket_vs_oracle(ctx, clip, params=None, batch_frames=8, min_clear=None, what="bracket"):
+    """A bracket against the oracle driven like F:1188-1242 on cv2 flows: cut flags, margin-guarded raw centres,
+    A5 (the device's smoothed centres equal oracle.motion_np.smooth_centers of the device's raw centres --
+    unconditionally), scalars with the device's centre against the oracle formula, and -- for every pair whose whole
+    +-6 window has clear argmax margins -- the scalar the oracle's own bracket loop produced.  Prints how many pairs
+    the margin guard covered; fails if fewer than `min_clear` pairs were compared without the guard."""
+    params = params or {}
+    vals, cuts, infos = mo.process_bracket(list(clip), params)
+    r = api.process_bracket(clip, params, ctx=ctx, batch_frames=batch_frames, return_flows=True)
+    n = len(infos)
+    assert r["n_pairs"] == n and np.array_equal(r["cut"], cuts), f"{what}: scene-cut flags differ"
+    gaps = np.zeros(n)
+    for j, info in enumerate(infos):
+        if j >= r["flow_first"]:
+            assert_flow_close(r["flows"][j - r["flow_first"]], info["flow"], f"{what} pair {j}")
+        gaps[j] = assert_argmax((r["cx"][j], r["cy"][j]), r["val"][j], info["flow"], f"{what} pair {j}")
+        ref = mo.radial_motion_weighted(info["flow"], r["centers"][j], info["cut"], bool(params.get("pov_mode", False)))
+        assert abs(r["scalar"][j] - ref) <= SCALAR_RTOL * abs(ref) + scalar_tol(info["flow"], r["centers"][j]), (what, j)
+    raw = np.stack([r["cx"], r["cy"]], 1)
+    assert np.array_equal(r["centers"], mo.smooth_centers(raw)), f"{what}: A5 smoothed centres differ from the oracle"
+    clear = gaps >= ARGMAX_MARGIN
+    window_clear = np.array([clear[max(0, j - 6):j + 7].all() for j in range(n)])
+    ref_raw = np.array([i["pos_center"] for i in infos])
+    assert np.array_equal(raw[clear], ref_raw[clear]), f"{what}: raw centres differ where the margin is clear"
+    for j in np.flatnonzero(window_clear):
+        assert abs(r["scalar"][j] - vals[j]) <= SCALAR_RTOL * abs(vals[j]) + scalar_tol(infos[j]["flow"], r["centers"][j]), (what, j)
+    print(f"{what}: {int((~clear).sum())} of {n} pairs under the argmax margin guard; {int(window_clear.sum())} scalars compared "
+          f"with the oracle's own bracket loop")
+    need = n // 2 if min_clear is None else min_clear
+    assert int(clear.sum()) >= need, f"{what}: only {int(clear.sum())} pairs with a clear argmax margin (need {need})"
+    return r, vals, cuts
 
 
 def check_batch_independence(ctx, width, height, n_frames=14, seed=9):

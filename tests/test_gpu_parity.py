@@ -118,39 +118,40 @@ def test_streaming_paths_agree(gpu_ctx):
 
 
 def test_bracket_vs_oracle_640x360(gpu_ctx):
-    """Config C1 geometry: per-pair centres (margin-guarded), cut flags and scalars vs the oracle."""
+    """Config C1 geometry: per-pair centres (margin-guarded, the count printed), cut flags, A5 and scalars vs the oracle."""
     clip = ClipGenerator(ClipSpec(640, 360, 24, seed=0, amplitude=0.15, period=30.0)).stack(3, 27)
-    vals, cuts, infos = mo.process_bracket(list(clip), {})
-    r = api.process_bracket(clip, {}, ctx=gpu_ctx, batch_frames=8, return_flows=True)
-    assert np.array_equal(r["cut"], cuts)
-    exact = 0
-    for j, info in enumerate(infos):
-        pc.assert_flow_close(r["flows"][j - r["flow_first"]], info["flow"], f"pair {j}") if j >= r["flow_first"] else None
-        exact += pc.assert_argmax((r["cx"][j], r["cy"][j]), r["val"][j], info["flow"], f"pair {j}") >= pc.ARGMAX_MARGIN
-        ref = mo.radial_motion_weighted(info["flow"], r["centers"][j], info["cut"])
-        assert abs(r["scalar"][j] - ref) <= pc.SCALAR_RTOL * abs(ref) + pc.scalar_tol(info["flow"], r["centers"][j])
-    assert exact >= len(infos) // 2
-    same = np.all(np.stack([r["cx"], r["cy"]], 1) == np.array([i["pos_center"] for i in infos]), axis=1)
-    if same.all():
-        assert np.allclose(r["scalar"], vals, rtol=pc.SCALAR_RTOL, atol=1e-6)
+    pc.check_bracket_vs_oracle(gpu_ctx, clip, batch_frames=8, what="C1 640x360")
 
 
 def test_bracket_vs_oracle_1080p(gpu_ctx):
-    """Config C2 geometry (the benchmarked size): centres (margin-guarded), cut flags, scalars."""
+    """Config C2 geometry (the benchmarked size): centres (margin-guarded), cut flags, A5, scalars."""
     clip = ClipGenerator(ClipSpec(1920, 1080, 18000, seed=0, amplitude=0.15, period=30.0)).stack(7, 14)
-    vals, cuts, infos = mo.process_bracket(list(clip), {})
-    r = api.process_bracket(clip, {}, ctx=gpu_ctx, batch_frames=4, return_flows=True)
-    assert r["n_pairs"] == 6 and np.array_equal(r["cut"], cuts)
-    exact = 0
-    for j, info in enumerate(infos):
-        print(pc.assert_flow_close(r["flows"][j - r["flow_first"]], info["flow"], f"1080p pair {j}"))
-        exact += pc.assert_argmax((r["cx"][j], r["cy"][j]), r["val"][j], info["flow"], f"pair {j}") >= pc.ARGMAX_MARGIN
-        ref = mo.radial_motion_weighted(info["flow"], r["centers"][j], info["cut"])
-        assert abs(r["scalar"][j] - ref) <= pc.SCALAR_RTOL * abs(ref) + pc.scalar_tol(info["flow"], r["centers"][j])
-    assert exact >= 3
-    same = np.all(np.stack([r["cx"], r["cy"]], 1) == np.array([i["pos_center"] for i in infos]), axis=1)
-    if same.all():
-        assert np.allclose(r["scalar"], vals, rtol=pc.SCALAR_RTOL, atol=1e-6)
+    pc.check_bracket_vs_oracle(gpu_ctx, clip, batch_frames=4, min_clear=3, what="C2 1080p")
+
+
+def test_c3_bracket_4k_pan_and_hard_cuts(gpu_ctx):
+    """Config C3 as BASELINE.json states it: 3840x2160, camera pan of 3 px per sampled frame, two hard scene cuts,
+    the reference's default threshold 7 (F:876), 14 pairs: identical scene-cut indices against cv2 (every pair at
+    least 0.05 px away from the threshold), cut pairs contribute exactly 0.0, centres / A5 / scalars as
+    in the other bracket tests."""
+    spec = ClipSpec(3840, 2160, 40, seed=3, amplitude=0.15, period=20.0, pan=(3.0, 0.0), cuts=(5, 10))
+    clip = ClipGenerator(spec).stack(0, 15)
+    r, vals, cuts = pc.check_bracket_vs_oracle(gpu_ctx, clip, {"cut_threshold": 7}, batch_frames=8, min_clear=4, what="C3 4K")
+    ref_mm = np.array([mo.mean_magnitude(cv2.calcOpticalFlowFarneback(a, b, None, 0.5, 3, 15, 3, 5, 1.2, 0))
+                       for a, b in zip(clip[:-1], clip[1:])])
+    assert (np.abs(ref_mm - 7.0) > 0.05).all(), f"clip no longer keeps every pair clear of the threshold: {ref_mm}"
+    assert np.flatnonzero(ref_mm > 7.0).tolist() == [4, 9], f"clip no longer has its two hard cuts: {ref_mm}"
+    assert np.flatnonzero(r["cut"]).tolist() == [4, 9]
+    assert np.allclose(r["mean_mag"], ref_mm, rtol=pc.MEAN_MAG_RTOL, atol=pc.MEAN_MAG_ATOL)
+    assert (r["scalar"][[4, 9]] == 0.0).all() and (r["scalar"][[0, 1, 2, 3, 5, 6, 7, 8]] != 0.0).all()
+
+
+def test_c4_bracket_vr_side_by_side(gpu_ctx):
+    """Config C4: 5760x2880 side-by-side frames (the largest per-frame working set: 332 MB of expansion per frame),
+    5 pairs through the bracket path: cut flags, centres, A5, scalars within 1e-3 of the oracle on cv2's flow."""
+    spec = ClipSpec(5760, 2880, 12, seed=6, amplitude=0.15, period=16.0, stereo=True)
+    clip = ClipGenerator(spec).stack(2, 8)
+    pc.check_bracket_vs_oracle(gpu_ctx, clip, batch_frames=4, min_clear=2, what="C4 5760x2880")
 
 
 def test_scene_cuts_and_pan(gpu_ctx):
@@ -294,3 +295,98 @@ def test_both_eyes_two_contexts_and_abort(gpu_ctx, tmp_path):
     again = api.process_bracket(gray, {}, ctx=gpu_ctx, batch_frames=4)
     for k in ("scalar", "cut", "cx", "cy", "val", "mean_mag"):
         assert np.array_equal(full[k], again[k]), k
+
+
+def test_multi_bracket_video_matches_race_free_reference(gpu_ctx, golden_dir, tmp_path):
+    """Several brackets end to end: the reference's process_video() with batch_size=30 on a 75-frame clip (brackets of
+    30, 30 and 15 frames), driven with its prefetch race neutralised (SURVEY Q3, F:1155-1185; the generating script
+    replaces threading.Thread by a synchronous stand-in), wrote tests/golden/video_multibracket.json; ours must write
+    the same keyframe timestamps.  No pair spans a bracket boundary and the +-6 window is cut at bracket ends."""
+    api.set_context(gpu_ctx)
+    g = json.load(open(os.path.join(golden_dir, "video_multibracket.json")))
+    s = g["spec"]
+    clip = ClipGenerator(ClipSpec(s["width"], s["height"], s["n_frames"], seed=s["seed"], amplitude=s["amplitude"],
+                                  period=s["period"])).stack()
+    path = str(tmp_path / "mb.avi")
+    vw = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"FFV1"), s["fps"], (s["width"], s["height"]), True)
+    if not vw.isOpened():
+        pytest.skip("FFV1 writer unavailable on this box")
+    for f in clip:
+        vw.write(cv2.cvtColor(f, cv2.COLOR_GRAY2BGR))
+    vw.release()
+    logs = []
+    assert runner.process_video(path, g["settings"], logs.append) is False, logs
+    acts = json.load(open(str(tmp_path / "mb.funscript")))["actions"]
+    assert [a["at"] for a in acts] == [a["at"] for a in g["actions"]], (acts, g["actions"])
+    assert max(abs(a["pos"] - b["pos"]) for a, b in zip(acts, g["actions"])) <= 1
+    res = runner.process_video_series(path, g["settings"], ctx=gpu_ctx)
+    assert res[2] == [i for a, b in g["brackets"] for i in range(a, b - 1)]      # 29 + 29 + 14 pairs, none across a boundary
+
+
+def test_integration_stub_from_the_docs_on_the_real_library(gpu_ctx):
+    """The ctypes stub INTEGRATION.md tells a reference maintainer to paste (replacement body of
+    precompute_flow_info_gpu, F:982-1017), executed as written against libffb.so on the GPU: the 8-key dict of
+    F:1008-1017 with the reference's types, equal to the shipped Python mirror's."""
+    import re
+    from funscript_flow_b200 import _native
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    code = re.search(r"```python\n(# --- in FunscriptFlow\.pyw.*?)```", text, re.S).group(1)
+    code = code.replace("/path/to/funscript_flow_b200/libffb.so", _native.DEFAULT_LIB)
+    ns = {}
+    exec(compile(code, "INTEGRATION.md", "exec"), ns)
+    clip = make_clip(320, 240, 3, seed=77, period=9.0, amplitude=0.3)
+    got = ns["precompute_flow_info_gpu"](clip[0], clip[1], 7)
+    api.set_context(gpu_ctx)
+    ours = api.precompute_flow_info_gpu(clip[0], clip[1], 7)
+    assert set(got) == set(ours) == {"flow", "pos_center", "neg_center", "val_pos", "val_neg", "cut", "cut_center", "mean_mag"}
+    assert np.array_equal(got["flow"], ours["flow"]) and got["flow"].dtype == np.float32
+    assert tuple(int(v) for v in got["pos_center"]) == tuple(int(v) for v in ours["pos_center"])
+    assert got["cut"] == ours["cut"] and isinstance(got["cut"], bool)
+    assert np.float32(got["val_pos"]) == np.float32(ours["val_pos"]) and np.float32(got["mean_mag"]) == np.float32(ours["mean_mag"])
+    ref = cv2.calcOpticalFlowFarneback(clip[0], clip[1], None, 0.5, 3, 15, 3, 5, 1.2, 0)
+    pc.assert_flow_close(got["flow"], ref, "INTEGRATION.md stub")
+
+
+def test_frame_range_shards_equal_the_single_bracket(gpu_ctx):
+    """Frame ranges of ONE bracket on separate contexts (one frame of overlap, raw centres exchanged between the
+    phases: ffb_bracket_begin_shard / phase1_finish / radial): every per-pair output equals the single-context
+    bracket bit for bit, at 1080p, for 2, 3 and 5 shards.  The shards run on every visible GPU in turn (one context
+    per shard), so on a multi-GPU box this also checks GPU-to-GPU reproducibility."""
+    from funscript_flow_b200 import _native
+    ngpu = _native.device_count()
+    clip = ClipGenerator(ClipSpec(1920, 1080, 18000, seed=0, amplitude=0.15, period=30.0)).stack(7, 7 + 41)
+    ref = api.process_bracket(clip, {}, ctx=gpu_ctx, batch_frames=16)
+    for parts in (2, 3, 5):
+        ctxs = [_native.FlowContext(i % ngpu) for i in range(parts)]
+        try:
+            got = api.process_bracket_on_contexts(clip, {}, ctxs, batch_frames=8)
+        finally:
+            for c in ctxs:
+                c.close()
+        for k in ("scalar", "cut", "cx", "cy", "val", "mean_mag", "centers"):
+            assert np.array_equal(ref[k], got[k]), (parts, k)
+
+
+def test_no_allocation_after_the_first_bracket(gpu_ctx, tmp_path):
+    """a video is configured once; brackets after the first one (the shorter last bracket included),
+    and per-pair drop-in calls of the same frame size in between, make no cudaMalloc / cudaHostAlloc."""
+    api.set_context(gpu_ctx)
+    clip = make_clip(640, 360, 50, seed=19, period=13.0, amplitude=0.3)
+    path = str(tmp_path / "v.avi")
+    vw = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"FFV1"), 30.0, (640, 360), True)
+    if not vw.isOpened():
+        pytest.skip("FFV1 writer unavailable on this box")
+    for f in clip:
+        vw.write(cv2.cvtColor(f, cv2.COLOR_GRAY2BGR))
+    vw.release()
+    prm = {"batch_size": 20, "vr_mode": False, "pov_mode": False, "native_resolution": True, "gpu_batch_frames": 8}
+    first = runner.process_video_series(path, prm, ctx=gpu_ctx)           # allocates for 640x360
+    base = gpu_ctx.alloc_counts()
+    again = runner.process_video_series(path, prm, ctx=gpu_ctx)           # brackets of 20, 20 and 10 frames: nothing new
+    assert gpu_ctx.alloc_counts() == base and again[0] == first[0]
+    info = api.precompute_flow_info(clip[0], clip[1], {})
+    api.radial_motion_weighted(info["flow"], info["pos_center"], info["cut"])
+    assert gpu_ctx.alloc_counts() == base
+    third = runner.process_video_series(path, prm, ctx=gpu_ctx)
+    assert gpu_ctx.alloc_counts() == base and third[0] == first[0]
