@@ -31,9 +31,15 @@ _contexts: Dict[int, _native.FlowContext] = {}
 
 
 def default_device() -> int:
-    for key in ("FFB_DEVICE", "LOCAL_RANK"):
-        if os.environ.get(key, "") != "":
-            return int(os.environ[key])
+    """FFB_DEVICE, else the torchrun LOCAL_RANK folded onto the visible devices (ranks may share a GPU), else 0."""
+    if os.environ.get("FFB_DEVICE", "") != "":
+        return int(os.environ["FFB_DEVICE"])
+    if os.environ.get("LOCAL_RANK", "") != "":
+        try:
+            n = _native.device_count()
+        except Exception:
+            n = 0
+        return int(os.environ["LOCAL_RANK"]) % max(1, n)
     return 0
 
 

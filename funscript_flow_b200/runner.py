@@ -210,13 +210,13 @@ def preprocess_plan(src_w: int, src_h: int, params: Dict, eye: Optional[str] = N
 
 def default_batch_frames(width: int, height: int) -> int:
     """Frames per GPU batch.  Small frames need many pairs per launch to fill 148 SMs (the reference's 256x256
-    product mode: 512), 1080p .. 4K run at full rate from 64, and above 4K the batch shrinks so that the
+    product mode: 512), 720p / 1080p take 128, 4K runs at full rate from 64, and above 4K the batch shrinks so that the
     per-batch device buffers (about 64 bytes per pixel and frame) stay near 35 GB."""
     px = max(1, width * height)
     if px <= 640 * 360:
         return 512
-    if px <= 1280 * 720:
-        return 128
+    if px <= 1920 * 1080:
+        return 128        # 1080p: +1.4 % over 64 (profiles/r2_sweep_flow_iter.txt), 17 GB of device buffers
     return max(2, min(64, int(64 * (3840 * 2160) / px)))
 
 

@@ -125,8 +125,8 @@ def test_bracket_vs_oracle_640x360(gpu_ctx):
 
 def test_bracket_vs_oracle_1080p(gpu_ctx):
     """Config C2 geometry (the benchmarked size): centres (margin-guarded), cut flags, A5, scalars."""
-    clip = ClipGenerator(ClipSpec(1920, 1080, 18000, seed=0, amplitude=0.15, period=30.0)).stack(7, 14)
-    pc.check_bracket_vs_oracle(gpu_ctx, clip, batch_frames=4, min_clear=3, what="C2 1080p")
+    clip = ClipGenerator(ClipSpec(1920, 1080, 18000, seed=0, amplitude=0.15, period=30.0)).stack(11, 19)   # the fast half of the stroke
+    pc.check_bracket_vs_oracle(gpu_ctx, clip, batch_frames=4, min_clear=4, what="C2 1080p")
 
 
 def test_c3_bracket_4k_pan_and_hard_cuts(gpu_ctx):
@@ -390,3 +390,98 @@ def test_no_allocation_after_the_first_bracket(gpu_ctx, tmp_path):
     assert gpu_ctx.alloc_counts() == base
     third = runner.process_video_series(path, prm, ctx=gpu_ctx)
     assert gpu_ctx.alloc_counts() == base and third[0] == first[0]
+
+
+def _torchrun(nproc, args, cwd, port, timeout=900):
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port)] + args
+    res = subprocess.run(cmd, cwd=cwd, env=env, capture_output=True, text=True, timeout=timeout)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    return res
+
+
+def test_run_headless_under_torchrun_matches_single_process(gpu_ctx, tmp_path):
+    """Row N3 / config C5 in miniature on real GPUs: `torchrun -m funscript_flow_b200 FOLDER` with one process per
+    GPU (two processes folded onto one GPU when only one is visible) deals the videos longest-first to the ranks
+    (F:2606-2638 per rank, run.<rank>.log) and writes the same funscripts as a single process; a second run skips every
+    file because the outputs exist (F:1105-1109)."""
+    from funscript_flow_b200 import _native
+    api.set_context(gpu_ctx)
+    nproc = max(2, min(4, _native.device_count()))
+    lengths = [40, 22, 31, 12]
+    for k, n in enumerate(lengths):
+        clip = make_clip(320, 240, n, seed=50 + k, period=9.0 + k, amplitude=0.3)
+        vw = cv2.VideoWriter(str(tmp_path / f"v{k}.avi"), cv2.VideoWriter_fourcc(*"FFV1"), 30.0, (320, 240), True)
+        if not vw.isOpened():
+            pytest.skip("FFV1 writer unavailable on this box")
+        for f in clip:
+            vw.write(cv2.cvtColor(f, cv2.COLOR_GRAY2BGR))
+        vw.release()
+    prm = {"threads": 8, "detrend_window": 2.0, "norm_window": 3.0, "batch_size": 3000, "overwrite": True, "vr_mode": False,
+           "pov_mode": False, "keyframe_reduction": True, "backend": "CUDA"}
+    cwd = os.getcwd()
+    os.chdir(str(tmp_path))
+    try:
+        assert runner.run_headless(str(tmp_path), prm, log_func=lambda m: None) == 0
+    finally:
+        os.chdir(cwd)
+    single = {k: json.load(open(str(tmp_path / f"v{k}.funscript"))) for k in range(4)}
+    for k in range(4):
+        (tmp_path / f"v{k}.funscript").unlink()
+    _torchrun(nproc, ["-m", "funscript_flow_b200", str(tmp_path), "--disable_keyframe_reduction", "--overwrite"], str(tmp_path), 29533)
+    multi = {k: json.load(open(str(tmp_path / f"v{k}.funscript"))) for k in range(4)}
+    assert multi == single
+    logs = [open(str(tmp_path / f"run.{r}.log")).read() for r in range(nproc)]
+    assert all("Batch processing complete." in l for l in logs)
+    assert sum(l.count("Funscript saved") for l in logs) == 4 and "v0.avi" in logs[0]      # the longest video goes to rank 0
+    res = _torchrun(nproc, ["-m", "funscript_flow_b200", str(tmp_path), "--disable_keyframe_reduction"], str(tmp_path), 29534)
+    assert res.stdout.count("Skipping: output file exists") == 4
+
+
+SHARD_WORKER = r"""
+import json, os, sys
+import numpy as np
+from funscript_flow_b200 import _native, api, distributed
+from funscript_flow_b200.synth import ClipGenerator, ClipSpec
+backend = sys.argv[2]
+rank, ws = distributed.init(backend)
+ctx = _native.FlowContext(api.default_device())
+api.set_context(ctx, api.default_device())
+clip = ClipGenerator(ClipSpec(1280, 720, 18000, seed=2, amplitude=0.2, period=24.0)).stack(5, 5 + 34)
+one = distributed.process_bracket_sharded(clip, {}, ctx=ctx, batch_frames=8)
+prm = {"batch_size": 12, "detrend_window": 2.0, "norm_window": 3.0, "keyframe_reduction": True, "gpu_batch_frames": 8}
+acts, series = distributed.process_frames_sharded(clip, 30.0, prm, ctx=ctx)
+if rank == 0:
+    json.dump({"one": {k: np.asarray(v).tolist() for k, v in one.items()}, "actions": acts, "values": series["values"].tolist(),
+               "ws": ws, "device": api.default_device()}, open(sys.argv[1], "w"))
+import torch.distributed as dist
+if dist.is_initialized():
+    dist.barrier(); dist.destroy_process_group()
+ctx.close()
+"""
+
+
+def test_bracket_sharded_over_ranks_on_gpus(gpu_ctx, tmp_path):
+    """SURVEY 8(e) on hardware: one 33-pair 720p bracket cut into frame ranges over the ranks of a torchrun job (NCCL
+    all-gather of the raw centres and of the scalars when every rank has its own GPU, gloo when ranks share one):
+    identical, bit for bit, to the single-process bracket; the same for a 3-bracket series with post-processing."""
+    from funscript_flow_b200 import _native
+    ngpu = _native.device_count()
+    nproc = max(2, min(4, ngpu))
+    backend = "nccl" if ngpu >= nproc else "gloo"
+    script = str(tmp_path / "worker.py")
+    open(script, "w").write(SHARD_WORKER)
+    _torchrun(nproc, [script, str(tmp_path / "multi.json"), backend], str(tmp_path), 29535)
+    multi = json.load(open(str(tmp_path / "multi.json")))
+    clip = ClipGenerator(ClipSpec(1280, 720, 18000, seed=2, amplitude=0.2, period=24.0)).stack(5, 5 + 34)
+    ref = api.process_bracket(clip, {}, ctx=gpu_ctx, batch_frames=16)
+    assert multi["ws"] == nproc and multi["one"]["n_pairs"] == 33
+    for k in ("scalar", "cut", "cx", "cy", "val", "mean_mag", "centers"):
+        assert np.array_equal(np.asarray(multi["one"][k]), np.asarray(ref[k]).tolist()), k
+    prm = {"batch_size": 12, "detrend_window": 2.0, "norm_window": 3.0, "keyframe_reduction": True, "gpu_batch_frames": 8}
+    acts, series = runner.process_frames(clip, 30.0, prm, ctx=gpu_ctx, return_series=True)
+    assert multi["values"] == series["values"].tolist() and multi["actions"] == acts
