@@ -458,7 +458,8 @@ int launch_upsample(ffb_ctx* c, const float2* src, size_t src_stride, int sp, in
 //   FFB_ITER_CFG=NTxUxHO   threads per CTA (= matrix columns per strip) x rows per step x outputs per horizontal task;
 //                          compiled in: 256x4x8, 128x2x4, 160x2x4 (the round-2 sweeps measured and dropped 96 / 192 /
 //                          512-thread strips, 8-output tasks on 2-row steps, 4-output tasks on 4-row steps, non-allocating
-//                          loads, bulk L2 prefetch and early issue of the second row pair: profiles/r2_sweep_flow_iter.txt)
+//                          loads, bulk L2 prefetch, early issue of the second row pair, and a barrier-free variant in which
+//                          neighbouring warps synchronise through shared-memory flags: profiles/r2_sweep_flow_iter.txt)
 //   FFB_ITER_CFG_K<k>      the same for pyramid level k only
 //   FFB_ITER_SH / FFB_ITER_MINSEG   rows per march segment (upper bound) / minimum segments per level
 //   FFB_ITER_SWMAX=0       equal-width strips (round 1) instead of full-width strips plus a narrow last one
@@ -1329,6 +1330,7 @@ static int flush_pending(ffb_ctx* c) {
 
 int ffb_bracket_push(ffb_ctx* c, const uint8_t* frames, int n, size_t pitch, size_t stride) {
     if (!c || !c->in_bracket) return fail(c, FFB_E_INVALID, "ffb_bracket_push outside a bracket");
+    CK(c, cudaSetDevice(c->device));      // several contexts (GPUs) may be driven by one host thread
     if (c->phase1_read) return fail(c, FFB_E_INVALID, "ffb_bracket_push after ffb_bracket_phase1_finish");
     if (!frames || n < 0 || pitch < (size_t)c->W || stride < pitch * (size_t)(c->H - 1) + c->W)
         return fail(c, FFB_E_INVALID, "ffb_bracket_push: bad arguments");
@@ -1361,6 +1363,7 @@ int ffb_bracket_abort(ffb_ctx* c) {
 
 int ffb_sync(ffb_ctx* c) {
     if (!c) return FFB_E_INVALID;
+    CK(c, cudaSetDevice(c->device));      // several contexts (GPUs) may be driven by one host thread
     CK(c, cudaStreamSynchronize(c->s_copy));
     CK(c, cudaStreamSynchronize(c->s_comp));
     return FFB_OK;
@@ -1407,6 +1410,7 @@ static int fetch_results(ffb_ctx* c, int n, bool with_radial, double* scalar, ui
 int ffb_bracket_finish(ffb_ctx* c, int* n_pairs, double* scalar, uint8_t* cut, int32_t* cx, int32_t* cy, float* val,
                        float* mean_mag, double* centers) {
     if (!c || !c->in_bracket) return fail(c, FFB_E_INVALID, "ffb_bracket_finish outside a bracket");
+    CK(c, cudaSetDevice(c->device));      // several contexts (GPUs) may be driven by one host thread
     if (c->deferred) return fail(c, FFB_E_INVALID, "shard bracket: use ffb_bracket_phase1_finish + ffb_bracket_radial");
     TRY(flush_pending(c));
     const int n = c->pairs_done;
@@ -1422,6 +1426,7 @@ int ffb_bracket_finish(ffb_ctx* c, int* n_pairs, double* scalar, uint8_t* cut, i
 int ffb_bracket_phase1_finish(ffb_ctx* c, int* n_pairs, int32_t* cx, int32_t* cy, float* val, float* mean_mag, uint8_t* cut) {
     if (!c || !c->in_bracket || !c->deferred)
         return fail(c, FFB_E_INVALID, "ffb_bracket_phase1_finish outside a bracket opened with ffb_bracket_begin_shard");
+    CK(c, cudaSetDevice(c->device));      // several contexts (GPUs) may be driven by one host thread
     TRY(flush_pending(c));
     c->phase1_read = true;
     if (n_pairs) *n_pairs = c->pairs_done;
@@ -1432,6 +1437,7 @@ int ffb_bracket_radial(ffb_ctx* c, const int32_t* cx_ext, const int32_t* cy_ext,
                        double* centers) {
     if (!c || !c->in_bracket || !c->deferred || !c->phase1_read)
         return fail(c, FFB_E_INVALID, "ffb_bracket_radial before ffb_bracket_phase1_finish");
+    CK(c, cudaSetDevice(c->device));      // several contexts (GPUs) may be driven by one host thread
     const int n = c->pairs_done;
     if (n > 0 && (!cx_ext || !cy_ext || first < 0 || first > 6 || n_ext < first + n || n_ext > first + n + 6))
         return fail(c, FFB_E_INVALID, "ffb_bracket_radial: %d external centres with the shard's first pair at %d do not frame %d pairs",
@@ -1457,6 +1463,7 @@ int ffb_flow_ring_size(const ffb_ctx* c) { return c ? c->ring_n : 0; }
 
 int ffb_bracket_get_flow(ffb_ctx* c, int pair, float* out) {
     if (!c || !out || c->W == 0) return FFB_E_INVALID;
+    CK(c, cudaSetDevice(c->device));      // several contexts (GPUs) may be driven by one host thread
     if (pair < 0 || pair >= c->pairs_done || pair < c->pairs_done - c->ring_n)
         return fail(c, FFB_E_RANGE, "flow of pair %d is not resident (pairs %d, ring %d)", pair, c->pairs_done, c->ring_n);
     CK(c, cudaStreamSynchronize(c->s_comp));
@@ -1740,6 +1747,7 @@ int ffb_preprocess_configure_window(ffb_ctx* c, int W, int H, int target_w, int 
 
 int ffb_bracket_push_bgr(ffb_ctx* c, const uint8_t* bgr, int n, size_t pitch, size_t stride) {
     if (!c || !c->in_bracket) return fail(c, FFB_E_INVALID, "ffb_bracket_push_bgr outside a bracket");
+    CK(c, cudaSetDevice(c->device));      // several contexts (GPUs) may be driven by one host thread
     if (c->phase1_read) return fail(c, FFB_E_INVALID, "ffb_bracket_push_bgr after ffb_bracket_phase1_finish");
     const ffb_ctx::PrePlan& pp = c->pre;
     if (pp.W == 0) return fail(c, FFB_E_INVALID, "ffb_bracket_push_bgr before ffb_preprocess_configure");

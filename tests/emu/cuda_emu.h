@@ -75,6 +75,7 @@ inline size_t g_smem_pool_cap = 0, g_smem_slice = 0;
 inline unsigned g_cluster_ctas = 1;
 inline unsigned long long g_warp_buf[512][32];   // shuffle exchange, per (cta, warp)
 inline long long g_launches = 0;
+inline unsigned long long g_spin_rounds = 0;
 constexpr size_t kStack = 256 * 1024;
 
 inline void fiber_entry() {
@@ -124,11 +125,12 @@ inline void run_cluster(unsigned nthreads, unsigned ncta, const uint3* bids) {
             g_dyn_smem = f.smem;
             swapcontext(&g_sched, &f.ctx);
         }
-        // every fiber is now waiting or done
-        unsigned done = 0, wcluster = 0;
+        // every fiber is now waiting, done, or still runnable (it polled a flag and yielded: ffb_spin_pause)
+        unsigned done = 0, wcluster = 0, runnable = 0;
         for (unsigned k = 0; k < total; ++k) {
             done += g_fibers[k].state == 3;
             wcluster += g_fibers[k].state == 4;
+            runnable += g_fibers[k].state == 0;
         }
         if (done == total) break;
         bool released = false;
@@ -162,6 +164,14 @@ inline void run_cluster(unsigned nthreads, unsigned ncta, const uint3* bids) {
             for (unsigned k = 0; k < total; ++k) if (g_fibers[k].state == 4) g_fibers[k].state = 0;
             released = true;
         }
+        if (!released && runnable) {          // pollers wait for one another: give them more rounds, but not forever
+            if (++g_spin_rounds > 50000000ull) {
+                fprintf(stderr, "cuda_emu: spin-wait never satisfied in block (%u,%u,%u)\n", g_blockIdx.x, g_blockIdx.y, g_blockIdx.z);
+                abort();
+            }
+            continue;
+        }
+        g_spin_rounds = 0;
         if (!released) {
             fprintf(stderr, "cuda_emu: deadlock / divergent barrier in block (%u,%u,%u)\n", g_blockIdx.x, g_blockIdx.y, g_blockIdx.z);
             abort();
@@ -233,6 +243,8 @@ inline T* map_shared(T* p, unsigned rank) {
 static constexpr int warpSize = 32;
 
 static inline void __syncthreads() { emu::yield_state(1); }
+static inline void __threadfence_block() {}
+static inline void __nanosleep(unsigned) { emu::yield_state(0); }      // a polling thread lets the others run
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu::yield_state(2); }
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) { return emu::shfl_generic(v, (emu::g_cur->linear % 32) ^ m); }
 template <class T> static inline T __shfl_down_sync(unsigned, T v, int d) {
