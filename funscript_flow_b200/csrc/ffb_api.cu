@@ -456,7 +456,7 @@ int launch_upsample(ffb_ctx* c, const float2* src, size_t src_stride, int sp, in
 // Tunables of the fused iteration kernel.  The defaults are compiled in; the environment overrides exist for
 // tuning runs and for the tests that force a variant onto small frames (parsed per launch):
 //   FFB_ITER_CFG=NTxUxHO   threads per CTA (= matrix columns per strip) x rows per step x outputs per horizontal task;
-//                          compiled in: 256x4x8, 128x2x4, 160x2x4 (the round-2 sweeps measured and dropped 96 / 192 /
+//                          compiled in: 256x4x8, 128x2x4, 160x2x4, 96x2x4, 64x2x4 (the round-2 sweeps measured and dropped 192 /
 //                          512-thread strips, 8-output tasks on 2-row steps, 4-output tasks on 4-row steps, non-allocating
 //                          loads, bulk L2 prefetch, early issue of the second row pair, and a barrier-free variant in which
 //                          neighbouring warps synchronise through shared-memory flags: profiles/r2_sweep_flow_iter.txt)
@@ -498,7 +498,8 @@ int launch_flow_iter_t(ffb_ctx* c, FfbIterArgs a, int npairs, int sh_target, dou
     // 14 halo rows: 2 (+7 % at 256x256, +3.5 % at 640x360) -- profiles/r1_sweep_segments.txt, r2_sweep_flow_iter.txt.
     // The rule looks at the frame the context is configured for, never at the batch.
     const long long frame_px = c->seg_frame_px > 0 ? c->seg_frame_px : (long long)w * h;      // stage hooks: the level itself
-    const int min_seg = min_seg_env > 0 ? min_seg_env : (frame_px >= 1280LL * 720 ? 3 : 2);
+    const int frame_w0 = c->seg_frame_px > 0 ? c->W : w;
+    const int min_seg = min_seg_env > 0 ? min_seg_env : (frame_px >= 1280LL * 720 ? 3 : (frame_w0 <= 320 ? 1 : 2));
     int nseg = (h + sh_target - 1) / sh_target;
     if (nseg < min_seg) nseg = min_seg;
     if (nseg > (h + 31) / 32) nseg = (h + 31) / 32;
@@ -558,21 +559,25 @@ int launch_flow_iter(ffb_ctx* c, FfbRing R, size_t plane, int rp, int w, int h, 
         //   1280x720 and larger   256 threads, 4 rows per step, 8 outputs per horizontal task: 242-column strips carry
         //                         5.5 % halo columns instead of 10.9 %, and the 120 horizontal tasks of a step fill 4 of
         //                         the 8 warps (1080p: +8.4 % over 128x2x4, 4K: +7 %, 720p: +1 %)
-        //   up to 320 columns     160 threads x 2 rows x 4 outputs (the reference's 256x256 product mode: 2 strips)
+        //   up to 320 columns     160 threads x 2 rows x 4 outputs (the reference's 256x256 product mode: 2 strips); its
+        //                         64- and 32-column levels take 96- and 64-thread strips (5 / 8 CTAs per SM instead of
+        //                         mostly idle 160-thread ones) and a single row segment per level: +3 % together
         //   in between            128 threads x 2 rows x 4 outputs (640x360: +8 % over 160x2x4)
         const long long frame_px = c->seg_frame_px > 0 ? c->seg_frame_px : (long long)w * h;
         const int frame_w = c->seg_frame_px > 0 ? c->W : w;
         if (frame_px >= 1280LL * 720) { nt = 256; u = 4; ho = 8; }
-        else if (frame_w <= 320) { nt = 160; u = 2; ho = 4; }
+        else if (frame_w <= 320) { nt = w <= 48 ? 64 : (w <= 80 ? 96 : 160); u = 2; ho = 4; }     // by LEVEL width
         else { nt = 128; u = 2; ho = 4; }
     }
     switch (nt * 100 + u * 10 + ho) {
         case 25648: return launch_flow_iter_t<256, 4, 2, 8>(c, a, npairs, k.sh, bytes);
         case 12824: return launch_flow_iter_t<128, 2, 4, 4>(c, a, npairs, k.sh, bytes);
         case 16024: return launch_flow_iter_t<160, 2, 3, 4>(c, a, npairs, k.sh, bytes);
+        case 9624:  return launch_flow_iter_t<96, 2, 5, 4>(c, a, npairs, k.sh, bytes);
+        case 6424:  return launch_flow_iter_t<64, 2, 8, 4>(c, a, npairs, k.sh, bytes);
         default: break;
     }
-    return fail(c, FFB_E_INVALID, "FFB_ITER_CFG: no k_flow_iter variant %dx%dx%d (compiled in: 256x4x8, 128x2x4, 160x2x4)", nt, u, ho);
+    return fail(c, FFB_E_INVALID, "FFB_ITER_CFG: no k_flow_iter variant %dx%dx%d (compiled in: 256x4x8, 128x2x4, 160x2x4, 96x2x4, 64x2x4)", nt, u, ho);
 }
 
 // ------------------------------------------------------------------ geometry

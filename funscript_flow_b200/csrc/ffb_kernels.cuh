@@ -938,7 +938,9 @@ __global__ void __launch_bounds__(256) k_divmag(FfbDivArgs a) {
     const int ylo = blockIdx.x * a.rows_per_block, yhi = min(ylo + a.rows_per_block, h);
     const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
     const int lane = threadIdx.x & 31;
-    unsigned long long best = 0ull;
+    // per-thread maximum as (|div| bits, pixel index): a thread visits its pixels in increasing index order, so a
+    // strict comparison keeps the first maximum; the 64-bit key is only built once at the end
+    unsigned best_a = 0u, best_i = 0u;
     double msum = 0.0;
     for (int y = ylo + ty; y < yhi; y += 4) {
         const float2* row = F + (size_t)y * fp;
@@ -967,6 +969,7 @@ __global__ void __launch_bounds__(256) k_divmag(FfbDivArgs a) {
             if (active) {
                 if (lane == 0 && x > 0) lft = __ldg(row + (x - 1)).y;
                 if (lane == 31 && x + 4 < w) rgt = __ldg(row + (x + 4)).y;
+                float m4 = 0.f;      // magnitudes of the (up to) 4 pixels, added in fp32 before they join the fp64 sum
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int xj = x + j;
@@ -977,16 +980,21 @@ __global__ void __launch_bounds__(256) k_divmag(FfbDivArgs a) {
                         const float xsc = (xj > 0 && xj < w - 1) ? 0.5f : 1.f;
                         const float gu = __fmul_rn(__fsub_rn(ubv[j], uav[j]), ysc);
                         const float gv = __fmul_rn(__fsub_rn(vr, vl), xsc);
-                        const float dv = __fadd_rn(gu, gv);
-                        const unsigned long long key = ((unsigned long long)__float_as_uint(fabsf(dv)) << 32) |
-                                                       (unsigned long long)(0xFFFFFFFFu - (unsigned)(y * w + xj));
-                        best = key > best ? key : best;
-                        msum += (double)sqrtf(__fmaf_rn(cxv[j], cxv[j], __fmul_rn(cyv[j], cyv[j])));
+                        const unsigned av = __float_as_uint(fabsf(__fadd_rn(gu, gv)));
+                        if (av > best_a) { best_a = av; best_i = (unsigned)(y * w + xj); }
+                        m4 = __fadd_rn(m4, sqrtf(__fmaf_rn(cxv[j], cxv[j], __fmul_rn(cyv[j], cyv[j]))));
                     }
                 }
+                msum += (double)m4;
             }
         }
     }
+    // (bits(|div|) << 32) | ~index: the largest key is the largest |div|, ties broken by the smallest index.  A thread
+    // that saw only zeros (or nothing) offers pixel 0 of ITS OWN range, which loses against any real pixel 0 tie-break
+    // only if its own first index is larger -- so it offers the smallest index it visited instead (or none).
+    const bool any = ylo + ty < yhi && 4 * tx < w;
+    if (best_a == 0u && any) best_i = (unsigned)((ylo + ty) * w + 4 * tx);
+    unsigned long long best = any ? (((unsigned long long)best_a << 32) | (unsigned long long)(0xFFFFFFFFu - best_i)) : 0ull;
     best = ffb_warp_max_u64(best);
     msum = ffb_warp_sum(msum);
     const int warp = threadIdx.x >> 5;

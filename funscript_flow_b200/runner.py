@@ -213,6 +213,8 @@ def default_batch_frames(width: int, height: int) -> int:
     product mode: 512), 720p / 1080p take 128, 4K runs at full rate from 64, and above 4K the batch shrinks so that the
     per-batch device buffers (about 64 bytes per pixel and frame) stay near 35 GB."""
     px = max(1, width * height)
+    if px <= 256 * 256:
+        return 1024       # the reference's product mode: +4 % over 512 (profiles/r2_sweep_flow_iter.txt), 4 GB of buffers
     if px <= 640 * 360:
         return 512
     if px <= 1920 * 1080:

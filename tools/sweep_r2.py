@@ -16,7 +16,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 KNOBS = ("FFB_ITER_CFG", "FFB_ITER_CFG_K0", "FFB_ITER_CFG_K1", "FFB_ITER_CFG_K2", "FFB_ITER_CFG_K3", "FFB_ITER_OPT", "FFB_ITER_SWMAX", "FFB_ITER_SH", "FFB_ITER_MINSEG",
-         "FFB_FLOW_STREAMS", "FFB_COPY_THREADS", "FFB_DIV", "FFB_PYR")
+         "FFB_FLOW_STREAMS", "FFB_COPY_THREADS", "FFB_RADIAL_STREAM")
 
 
 def main():
