@@ -2,9 +2,9 @@
 //
 // One context = one GPU = one host thread.  Frames flow
 //   host (pageable | pinned) --cudaMemcpyAsync on s_copy, double-buffered--> device u8 staging
-//   --k_pyramid_level / k_polyexp--> per-frame expansion slots (ring of B+1 frames; each frame is
-//     expanded once and used as `next` of pair j-1 and `prev` of pair j: streaming mode)
-//   --k_upsample_flow / k_flow_iter x3 per level--> final-flow ring (B+8 pairs)
+//   --k_pyramid_pow2 | k_pyramid_level / k_polyexp--> per-frame expansion slots (ring of S = B+2 frames; each frame
+//     is expanded once and used as `next` of pair j-1 and `prev` of pair j: streaming mode)
+//   --k_flow_iter x3 per level (flow up-sampling fused, k_upsample_flow otherwise)--> final-flow ring (>= B+8 pairs)
 //   --k_divmag / k_phase1_finish--> per-pair centre, value, mean magnitude, cut flag (device arrays)
 //   --k_smooth_centers / k_radial / k_radial_finish (lagging 6 pairs)--> per-pair scalar
 // and only the 1-D per-pair results are copied back at ffb_bracket_finish.
@@ -1590,7 +1590,7 @@ int ffb_stage_pyramid(ffb_ctx* c, const uint8_t* img, int W, int H, size_t pitch
     pyramid_window(xi, w, W, PYR_TW, taps.r, &RW);
     pyramid_window(yi, h, H, PYR_TH, taps.r, &RH);
     Scratch s;
-    uint8_t* d_img; float* d_out; int *dxi, *dyi; float *dxa, *dya;
+    uint8_t* d_img = nullptr; float* d_out = nullptr; int *dxi = nullptr, *dyi = nullptr; float *dxa = nullptr, *dya = nullptr;
     TRY(s.alloc(c, &d_img, (size_t)W * H));
     CK(c, cudaMemcpy2D(d_img, W, img, pitch, W, H, cudaMemcpyHostToDevice));
     if (pyramid_fast_ok(W, H, p)) {   // the production path for this geometry: all levels in one pass
@@ -1643,7 +1643,7 @@ int ffb_stage_polyexp(ffb_ctx* c, const float* img, int w, int h, float* out) {
     Scratch s;
     const int rp = ffb_round_up(w, 4);            // the kernel stores 16-byte vectors
     const size_t plane = (size_t)rp * h;
-    float *d_in, *d_out;
+    float *d_in = nullptr, *d_out = nullptr;
     TRY(s.upload(c, &d_in, img, (size_t)w * h));
     TRY(s.alloc(c, &d_out, 5 * plane));
     FfbRing dst{(char*)d_out, 0, 0, 1};
@@ -1659,7 +1659,7 @@ int ffb_stage_update_matrices(ffb_ctx* c, const float* R0, const float* R1, cons
     if (!c || !R0 || !R1 || !out) return FFB_E_INVALID;
     CK(c, cudaSetDevice(c->device));
     Scratch s;
-    float *d0, *d1, *dM; float2* df = nullptr;
+    float *d0 = nullptr, *d1 = nullptr, *dM = nullptr; float2* df = nullptr;
     TRY(s.upload(c, &d0, R0, (size_t)5 * w * h));
     TRY(s.upload(c, &d1, R1, (size_t)5 * w * h));
     if (flow) TRY(s.upload(c, &df, (const float2*)flow, (size_t)w * h));
@@ -1680,7 +1680,7 @@ int ffb_stage_flow_iter(ffb_ctx* c, const float* R0, const float* R1, const floa
     Scratch s;
     const int rp = ffb_round_up(w, 4);
     const size_t plane = (size_t)rp * h;
-    float* dR; float2 *dfi = nullptr, *dfo;
+    float* dR = nullptr; float2 *dfi = nullptr, *dfo = nullptr;
     TRY(s.alloc(c, &dR, 10 * plane));
     for (int f = 0; f < 2; ++f) {
         std::vector<float> host;
@@ -1708,7 +1708,7 @@ int ffb_stage_upsample_flow(ffb_ctx* c, const float* flow_c, int wc, int hc, int
     make_linear_table(w, wc, xi, xa);
     make_linear_table(h, hc, yi, ya);
     Scratch s;
-    float2 *dsrc, *ddst; int *dxi, *dyi; float *dxa, *dya;
+    float2 *dsrc = nullptr, *ddst = nullptr; int *dxi = nullptr, *dyi = nullptr; float *dxa = nullptr, *dya = nullptr;
     TRY(s.upload(c, &dsrc, (const float2*)flow_c, (size_t)wc * hc));
     TRY(s.alloc(c, &ddst, (size_t)w * h));
     TRY(s.upload(c, &dxi, xi.data(), xi.size())); TRY(s.upload(c, &dxa, xa.data(), xa.size()));
@@ -1809,8 +1809,8 @@ static int stage_preprocess_plan(ffb_ctx* c, const uint8_t* bgr, size_t pitch, c
     if (!c || !bgr || !gray || !plan_ok(p) || pitch < (size_t)p.W * 3) return fail(c, FFB_E_INVALID, "ffb_stage_preprocess: bad arguments");
     CK(c, cudaSetDevice(c->device));
     Scratch s;
-    uint8_t *d_src, *d_dst;
-    int *dxt, *dyt;
+    uint8_t *d_src = nullptr, *d_dst = nullptr;
+    int *dxt = nullptr, *dyt = nullptr;
     const std::vector<int> xt = make_u8_resize_table(p.TW, p.W, true), yt = make_u8_resize_table(p.TH, p.H, false);
     TRY(s.alloc(c, &d_src, (size_t)p.W * p.H * 3));
     CK(c, cudaMemcpy2D(d_src, (size_t)p.W * 3, bgr, pitch, (size_t)p.W * 3, p.H, cudaMemcpyHostToDevice));

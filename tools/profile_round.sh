@@ -1,10 +1,11 @@
 #!/bin/bash
 # Round evidence on the GPU box: default bench line, ncu launch list, and one `ncu --set full` capture per
 # kernel of the hot path.  Usage (through gpurun): tools/profile_round.sh TAG  -> gpurun_out/*_TAG.*
-# The captures run with one flow stream so that every launch covers the whole batch (64 pairs / 65 frames).
+# The captures run with one flow stream so that every launch covers the whole batch (128 pairs / 129 frames at 1080p).
+# Afterwards, here: python tools/make_traffic_json.py gpurun_out/prof_iter_TAG.ncu-rep gpurun_out/bench_TAG.json
 set -u
 TAG=${1:-rX}
-B="python bench.py --steps 2 --warmup 1 --no-cpu-baseline"
+B="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extras"
 mkdir -p gpurun_out
 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err || { echo "bench failed"; tail -5 gpurun_out/bench_$TAG.err; exit 1; }
 $B > gpurun_out/plain_$TAG.log 2>&1 || { echo "short bench failed"; exit 1; }     # exits 0 without ncu first
