@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--batch-frames", type=int, default=0, help="0 = runner.default_batch_frames(width, height)")
     ap.add_argument("--strong-pairs", type=int, default=1536, help="c2-strong: pairs of the one bracket that is split")
     ap.add_argument("--c5-videos", type=int, default=64)
+    ap.add_argument("--c5-pageable", action="store_true", help="c5: clips in ordinary (pageable) NumPy memory instead of pinned buffers")
     ap.add_argument("--cpu-sample-pairs", type=int, default=0, help="0 = 2 x host cores (bounded to 8..64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the pageable / drop-in / per-level side measurements")
@@ -544,7 +545,18 @@ def run_c5(args, rank, world, local, dd, numa_node):
     for v in mine:
         need.setdefault(v % 4, 0)
         need[v % 4] = max(need[v % 4], (v // 4) * 3 + lengths[v])
-    bases = {s: ClipGenerator(ClipSpec(W, H, 18000, seed=s, amplitude=0.15, period=30.0)).stack(0, n) for s, n in need.items()}
+    # the clips live in page-locked host memory, as a decoder that writes into buffers from ffb_host_alloc would leave
+    # them (frames DMA straight out of them; --c5-pageable keeps them in ordinary NumPy memory instead, which adds the
+    # library's staging memcpy -- the host-side limiter when 8 processes do it at once, profiles/r2_scaling.txt)
+    bases, pins = {}, []
+    for sd, n in need.items():
+        arr = ClipGenerator(ClipSpec(W, H, 18000, seed=sd, amplitude=0.15, period=30.0)).stack(0, n)
+        if not args.c5_pageable:
+            pb = _native.PinnedBuffer(arr.shape)
+            pb.array[...] = arr
+            pins.append(pb)
+            arr = pb.array
+        bases[sd] = arr
     vids = {v: bases[v % 4][(v // 4) * 3:(v // 4) * 3 + lengths[v]] for v in mine}
     ctx = _native.FlowContext(local)
     api.set_context(ctx, api.default_device())
@@ -590,9 +602,10 @@ def run_c5(args, rank, world, local, dd, numa_node):
                 "dtype": "f32", "data": "synthetic", "config": bench_config(args, world),
                 "run": {"numa_node": numa_node, "videos": NV, "pairs_per_step": pairs, "frames_per_rank": loads,
                         "schedule": "longest-first", "kernels_sha": kernels_sha(),
-                        "timing": "wall clock, pageable host frames through runner.process_frames (H2D, post-processing and the object gather inside)"},
+                        "host_memory": "pageable" if args.c5_pageable else "pinned",
+                        "timing": "wall clock, host frames through runner.process_frames (H2D, post-processing and the object gather inside)"},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(sum(lengths) * W * H), "d2h_bytes_per_step": int(pairs * 41),
-                        "ms_per_step": 1000 * wall / steps, "source": "pageable host frames"},
+                        "ms_per_step": 1000 * wall / steps, "source": ("pageable" if args.c5_pageable else "pinned") + " host frames"},
                 "gpu_launches": int(ctx.launch_count - l0), "clocks": clocks,
                 "roofline": {"bound": "hbm", "kernel": "whole path", "achieved": WHOLE_PATH_B_PER_PX * W * H * value / world / 1e9,
                              "peak": peak, "unit": "GB/s", "frac": WHOLE_PATH_B_PER_PX * W * H * value / world / 1e9 / peak,

@@ -1314,14 +1314,17 @@ int ffb_bracket_begin_shard(ffb_ctx* c, int pov, double thr, int shard_pairs) {
 
 // Frames the next batch of the bracket may take.
 static int batch_cap(const ffb_ctx* c, PtrKind kind) {
-    // a bracket of k*B pairs has k*B + 1 frames: let its first batch take B + 1 frames (B pairs)
+    // a bracket of k*B pairs has k*B + 1 frames: let its first batch take one frame more
     // so that no degenerate one-frame batch is left over
-    if (c->frames_seen != 0) return c->B;
-    // host input: keep the first batch of a bracket small so that compute starts after a short upload and
-    // every later upload hides behind the previous batch's kernels (B/4 + 1 measured best at 1080p: B/2 + 1
-    // and B/8 + 1 lose 3 %, a B/8+1, 3B/8, B ramp 1 % end to end)
-    if (kind != PTR_DEVICE && c->B >= 8) return c->B / 4 + 1;
-    return c->B + 1;
+    if (kind == PTR_DEVICE || c->B < 16) return c->frames_seen == 0 ? c->B + 1 : c->B;
+    // Host input: the upload of batch i+1 hides behind the kernels of batch i only while it is not longer than
+    // them.  A GPU consumes 1080p frames at ~15 GB/s and receives them at 25 .. 55 GB/s (eight GPUs uploading at
+    // once share the host's memory and PCIe roots), so batches may grow by a factor of two, not more: B/4 + 1, B/2,
+    // B, B, ...  (with a jump from B/4 + 1 straight to B = 128 the second upload took ~10 ms against 4.4 ms of
+    // kernels on an 8-GPU box: end-to-end 0.84 of device-resident; a ramp from B/8 + 1 costs 1.4 % on one GPU because
+    // of its small batches -- profiles/r2_scaling.txt).  A 3000-frame bracket pays this ramp once.
+    if (c->frames_seen == 0) return c->B / 4 + 1;
+    return c->frames_seen <= c->B / 4 + 1 ? c->B / 2 : c->B;
 }
 
 // ffb_bracket_push_bgr gathers pre-processed gray frames in the device staging buffer until a batch is full;
