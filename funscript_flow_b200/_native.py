@@ -59,6 +59,7 @@ def load(path: Optional[str] = None) -> C.CDLL:
         "ffb_bracket_push": (i32, [vp, vp, i32, sz, sz]),
         "ffb_bracket_finish": (i32, [vp, i32p, f64p, u8p, i32p, i32p, f32p, f32p, f64p]),
         "ffb_sync": (i32, [vp]),
+        "ffb_chain_after": (i32, [vp, vp]),
         "ffb_bracket_abort": (i32, [vp]),
         "ffb_bracket_get_flow": (i32, [vp, i32, f32p]),
         "ffb_flow_ring_size": (i32, [vp]),
@@ -318,6 +319,10 @@ class FlowContext:
         res["cut"] = res["cut"].astype(bool)
         res["n_pairs"] = k
         return res
+
+    def chain_after(self, earlier: "FlowContext"):
+        """Kernels queued on this context from now on start after everything `earlier` (same device) has queued."""
+        self._ck(self._lib.ffb_chain_after(self._h, earlier._h))
 
     def sync(self):
         self._ck(self._lib.ffb_sync(self._h))

@@ -181,6 +181,55 @@ def process_bracket_on_contexts(frames, params: Optional[Dict], ctxs: Sequence[_
     return cat
 
 
+class BracketPipeline:
+    """Consecutive brackets (of one video, or the clips of a library) pipelined over two contexts of one GPU: bracket
+    i+1 is pushed -- its frames start uploading -- before the results of bracket i are fetched, so the upload of the
+    first batch and the drain of the last one no longer sit between brackets.  The kernels of the two contexts are
+    chained (ffb_chain_after), only uploads overlap.  Results are those of process_bracket, bit for bit.
+
+        pipe = BracketPipeline(ctx)
+        for frames in brackets:
+            done = pipe.submit(frames, params)      # returns the result of the bracket submitted before, or None
+        last = pipe.flush()
+
+    Host frames (pinned or pageable) must stay valid until their bracket's result has been returned."""
+
+    def __init__(self, ctx: Optional[_native.FlowContext] = None, batch_frames: int = DEFAULT_BATCH_FRAMES):
+        primary = ctx or get_context()
+        self.ctxs = [primary, get_aux_context(primary)]
+        self.batch_frames = batch_frames
+        self._turn = 0
+        self._pending = None        # (context, keep-alive array) of the bracket whose result has not been fetched
+
+    def submit(self, frames, params: Optional[Dict] = None):
+        params = params or {}
+        arr = _as_frames(frames)
+        n, h, w = arr.shape
+        ctx = self.ctxs[self._turn]
+        other = self.ctxs[self._turn ^ 1]
+        ctx.configure(w, h, max(1, min(self.batch_frames, n)), max(n - 1, 1))
+        if self._pending is not None:
+            ctx.chain_after(other)
+        ctx.bracket_begin(bool(params.get("pov_mode", False)), float(params.get("cut_threshold", DEFAULT_CUT_THRESHOLD)))
+        try:
+            ctx.bracket_push(arr)
+        except BaseException:
+            ctx.bracket_abort()
+            raise
+        done = self.flush()
+        self._pending = (ctx, arr)
+        self._turn ^= 1
+        return done
+
+    def flush(self):
+        """Result of the bracket submitted last (None when there is none)."""
+        if self._pending is None:
+            return None
+        ctx, _ = self._pending
+        self._pending = None
+        return ctx.bracket_finish()
+
+
 def precompute_flow_info(p0: np.ndarray, p1: np.ndarray, config: Dict) -> Dict:
     """F:843-907.  `config["backend"]` is ignored (there is one backend); `pov_mode` and the
     hidden `cut_threshold` key are honoured like the CPU branch (F:876-894)."""

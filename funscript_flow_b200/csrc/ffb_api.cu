@@ -191,6 +191,7 @@ struct ffb_ctx {
     cudaStream_t s_time = nullptr;                     // only carries the end-of-flow-phase timing event
     cudaEvent_t ev_flow_end[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_chain = nullptr;                    // "everything queued on s_comp so far": ffb_chain_after
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_expand[2] = {nullptr, nullptr};
     FfbPolyConsts poly;
     // geometry
@@ -1197,6 +1198,7 @@ int ffb_create(int device, ffb_ctx** out) {
         return rc;
     }
     cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_chain, cudaEventDisableTiming);
     cudaStreamCreateWithFlags(&c->s_time, cudaStreamNonBlocking);
     for (int i = 0; i < 4; ++i) cudaEventCreateWithFlags(&c->ev_flow_end[i], cudaEventDisableTiming);
     for (int i = 0; i < 3; ++i) {
@@ -1237,6 +1239,7 @@ void ffb_destroy(ffb_ctx* c) {
         cudaEventDestroy(c->ev_ch2d[b]); cudaEventDestroy(c->ev_pre[b]);
     }
     cudaEventDestroy(c->ev_fork);
+    cudaEventDestroy(c->ev_chain);
     for (int i = 0; i < 4; ++i) cudaEventDestroy(c->ev_flow_end[i]);
     cudaStreamDestroy(c->s_time);
     for (int i = 0; i < 3; ++i) { cudaEventDestroy(c->ev_join[i]); cudaStreamDestroy(c->s_aux[i]); }
@@ -1366,6 +1369,16 @@ int ffb_bracket_abort(ffb_ctx* c) {
     c->deferred = c->phase1_read = false;
     c->pend = 0;
     c->frames_seen = c->pairs_done = c->radial_done = 0;
+    return FFB_OK;
+}
+
+int ffb_chain_after(ffb_ctx* later, ffb_ctx* earlier) {
+    if (!later || !earlier || later == earlier) return FFB_E_INVALID;
+    if (later->device != earlier->device) return fail(later, FFB_E_INVALID, "ffb_chain_after: contexts on different devices");
+    CK(later, cudaSetDevice(later->device));
+    // the kernels `later` queues from now on start after everything `earlier` has queued so far; uploads (s_copy) do not wait
+    CK(later, cudaEventRecord(earlier->ev_chain, earlier->s_comp));
+    CK(later, cudaStreamWaitEvent(later->s_comp, earlier->ev_chain, 0));
     return FFB_OK;
 }
 

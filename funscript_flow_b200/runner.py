@@ -36,29 +36,61 @@ def _brackets(n_frames: int, bracket: int):
             yield a, b
 
 
+def process_many(clips: Sequence, fps: float, params: Dict, ctx=None, return_series: bool = False,
+                 progress_callback: Optional[Callable[[int], None]] = None, cancel_flag: Optional[Callable[[], bool]] = None):
+    """The bracket loop (F:1145-1253) + post-processing (F:1266-1386) over several in-memory clips (each a sequence of
+    sampled gray frames, or a (frames, frame_indices) tuple), with ALL their brackets pipelined over two contexts of the
+    GPU (api.BracketPipeline): the frames of the next bracket -- of the same clip or of the next one -- upload while
+    the current one computes.  Returns one entry per clip: actions, or (actions, series) with return_series.
+    Per-bracket results are those of api.process_bracket, bit for bit."""
+    bracket = int(params.get("batch_size", 3000.0))
+    pipe = api.BracketPipeline(ctx, batch_frames=int(params.get("gpu_batch_frames", api.DEFAULT_BATCH_FRAMES)))
+    items = []                      # per clip: frames, frame indices, list of bracket bounds
+    for clip in clips:
+        frames, idx = clip if isinstance(clip, tuple) else (clip, None)
+        n = len(frames)
+        items.append((frames, list(range(n)) if idx is None else list(idx), list(_brackets(n, bracket))))
+    acc = [dict(values=[], cuts=[], stamps=[]) for _ in items]
+    order = [(k, a, b) for k, (_, _, br) in enumerate(items) for a, b in br]
+    total = max(1, len(order))
+
+    def take(res, k, a, b):
+        acc[k]["values"].extend(res["scalar"].tolist())
+        acc[k]["cuts"].extend(res["cut"].tolist())
+        acc[k]["stamps"].extend(items[k][1][a:b - 1])          # F:1151: frame index of the first frame of each pair
+    prev = None
+    for j, (k, a, b) in enumerate(order):
+        if cancel_flag and cancel_flag():
+            pipe.flush()
+            return None
+        done = pipe.submit(items[k][0][a:b], params)
+        if prev is not None:
+            take(done, *prev)
+        prev = (k, a, b)
+        if progress_callback:
+            progress_callback(min(100, int(100 * (j + 1) / total)))
+    if prev is not None:
+        take(pipe.flush(), *prev)
+    out = []
+    for k in range(len(items)):
+        v = acc[k]
+        actions = postproc.scalars_to_actions(v["values"], v["cuts"], v["stamps"], fps, params) if v["values"] else []
+        if return_series:
+            out.append((actions, dict(values=np.asarray(v["values"]), cuts=np.asarray(v["cuts"], bool),
+                                      frame_indices=np.asarray(v["stamps"]))))
+        else:
+            out.append(actions)
+    return out
+
+
 def process_frames(frames: Sequence[np.ndarray], fps: float, params: Dict, frame_indices: Optional[Sequence[int]] = None,
                    ctx=None, progress_callback: Optional[Callable[[int], None]] = None,
                    cancel_flag: Optional[Callable[[], bool]] = None, return_series: bool = False):
-    """Bracket loop (F:1145-1253) + post-processing (F:1266-1386) over in-memory sampled frames."""
-    n = len(frames)
-    idx = list(range(n)) if frame_indices is None else list(frame_indices)
-    bracket = int(params.get("batch_size", 3000.0))
-    values: List[float] = []
-    cuts: List[bool] = []
-    stamps: List[int] = []
-    for a, b in _brackets(n, bracket):
-        if cancel_flag and cancel_flag():
-            return None
-        r = api.process_bracket(frames[a:b], params, ctx=ctx, batch_frames=int(params.get("gpu_batch_frames", api.DEFAULT_BATCH_FRAMES)))
-        values.extend(r["scalar"].tolist())
-        cuts.extend(r["cut"].tolist())
-        stamps.extend(idx[a:b - 1])          # F:1151: frame index of the first frame of each pair
-        if progress_callback:
-            progress_callback(min(100, int(100 * b / n)))
-    actions = postproc.scalars_to_actions(values, cuts, stamps, fps, params) if values else []
-    if return_series:
-        return actions, dict(values=np.asarray(values), cuts=np.asarray(cuts, bool), frame_indices=np.asarray(stamps))
-    return actions
+    """Bracket loop (F:1145-1253) + post-processing (F:1266-1386) over in-memory sampled frames (one clip of
+    process_many: consecutive brackets are pipelined over two contexts of the GPU)."""
+    res = process_many([(frames, frame_indices)], fps, params, ctx=ctx, return_series=return_series,
+                       progress_callback=progress_callback, cancel_flag=cancel_flag)
+    return None if res is None else res[0]
 
 
 def _container_shape(cap):

@@ -122,6 +122,12 @@ int  ffb_bracket_radial(ffb_ctx* ctx, const int32_t* cx_ext, const int32_t* cy_e
  * waits for the device work already queued, then leaves the context ready for ffb_bracket_begin /
  * ffb_configure.  A no-op outside a bracket. */
 int  ffb_bracket_abort(ffb_ctx* ctx);
+/* Two contexts on one device used alternately pipeline consecutive brackets: the frames of bracket i+1 are pushed
+ * (uploaded on its context's copy stream) while bracket i still computes, and the results of bracket i are fetched
+ * afterwards.  ffb_chain_after(later, earlier) orders the KERNELS `later` queues from now on behind everything
+ * `earlier` has queued so far (the two contexts' kernels would otherwise run side by side and compete for the SMs);
+ * uploads are not delayed.  Results do not depend on it. */
+int  ffb_chain_after(ffb_ctx* later, ffb_ctx* earlier);
 /* Block until all uploads issued so far have left the caller's buffers. */
 int  ffb_sync(ffb_ctx* ctx);
 /* Copy the final flow field of pair `pair` of the current / last bracket to host (test hook and

@@ -432,3 +432,34 @@ def test_colour_pushes_gather_into_full_batches(emu_lib):
     ref = api.process_bracket(gray, {}, ctx=ctx, batch_frames=8)
     assert np.array_equal(ref["scalar"], whole["scalar"])
     ctx.close()
+
+
+def test_bracket_pipeline_equals_single_brackets(emu_lib):
+    """api.BracketPipeline (two contexts alternating, kernels chained with ffb_chain_after, uploads overlapping) returns
+    for every bracket what api.process_bracket returns, bit for bit, in submission order -- brackets of different
+    lengths and frame sizes, POV parameters per bracket, an empty tail; runner.process_many keeps the clips apart."""
+    from funscript_flow_b200 import _native
+    ctx = _native.FlowContext(0, emu_lib)
+    single = _native.FlowContext(0, emu_lib)
+    clips = [make_clip(96, 64, 9, seed=1), make_clip(96, 64, 4, seed=2), make_clip(80, 48, 6, seed=3), make_clip(96, 64, 2, seed=4)]
+    prms = [{}, {"pov_mode": True}, {"cut_threshold": 0.01}, {}]
+    pipe = api.BracketPipeline(ctx, batch_frames=4)
+    got = []
+    for c, p in zip(clips, prms):
+        done = pipe.submit(c, p)
+        if done is not None:
+            got.append(done)
+    got.append(pipe.flush())
+    assert pipe.flush() is None and len(got) == len(clips)
+    for c, p, g in zip(clips, prms, got):
+        ref = api.process_bracket(c, p, ctx=single, batch_frames=4)
+        for k in ("scalar", "cut", "cx", "cy", "val", "mean_mag", "centers"):
+            assert np.array_equal(ref[k], g[k]), k
+    prm = {"batch_size": 4, "detrend_window": 2.0, "norm_window": 3.0, "keyframe_reduction": False, "gpu_batch_frames": 3}
+    many = runner.process_many([clips[0], clips[1]], 30.0, prm, ctx=ctx, return_series=True)
+    for clip, (acts, series) in zip(clips[:2], many):
+        a1, s1 = runner.process_frames(clip, 30.0, prm, ctx=single, return_series=True)
+        assert acts == a1 and np.array_equal(series["values"], s1["values"]) and np.array_equal(series["frame_indices"], s1["frame_indices"])
+    with pytest.raises(_native.FFBError):
+        ctx.chain_after(ctx)
+    ctx.close(); single.close()
