@@ -392,9 +392,17 @@ def test_no_allocation_after_the_first_bracket(gpu_ctx, tmp_path):
     assert gpu_ctx.alloc_counts() == base and third[0] == first[0]
 
 
-def _torchrun(nproc, args, cwd, port, timeout=900):
+def _free_port():
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
+
+
+def _torchrun(nproc, args, cwd, port=None, timeout=900):
     import subprocess
     import sys
+    port = _free_port()          # a fixed port could collide with another job on the box
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",

@@ -44,6 +44,10 @@ def run(nproc, emu_lib, out, port):
         env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
         subprocess.run([sys.executable, path], check=True, env=env, timeout=600)
     else:
+        import socket
+        with socket.socket() as sk:      # a free port instead of a fixed one (another job on the box may hold it)
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
         subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
                         "--master-addr", "127.0.0.1", "--master-port", str(port), path], check=True, timeout=900)
     return json.load(open(out))
