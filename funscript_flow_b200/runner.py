@@ -20,7 +20,7 @@ from __future__ import annotations
 import math
 import os
 import time
-from typing import Callable, Dict, Iterable, List, Optional, Sequence
+from typing import Callable, Dict, List, Optional, Sequence
 
 import numpy as np
 
